@@ -1,0 +1,154 @@
+/*
+ * mflbm.h -- C ABI of the B200-native MF-LBM time-step hot path.
+ *
+ * This is the drop-in boundary: the reference (lanl/MF-LBM, Fortran 90 + OpenACC + MPI) keeps its
+ * driver, control files, geometry loading and output formats and calls these entry points through
+ * ISO_C_BINDING in place of its kernel subroutines (binding: fortran/mflbm_iso_c.f90).
+ * The reference has no FFI of its own; every export names the reference routine / call site it
+ * replaces ("MP/" = multiphase_3D/0.src/, "SP/" = singlephase_3D/0.src/).
+ *
+ * Conventions
+ *  - every call returns int: 0 = ok, <0 = error (text via mflbm_last_error); the Fortran wrapper maps
+ *    non-zero to MPI_Barrier + mpi_abort like MP/IO_multiphase.F90:543-545.
+ *  - host arrays are caller-owned, contiguous, column-major (i fastest) with the reference's ghost
+ *    extents (MP/Init_multiphase.F90:594-658): PDFs/u/v/w/rho/curv (0:nx+1,0:ny+1,0:nz+1);
+ *    cn_x,cn_y,cn_z,c_norm and walls(int8) (-1:nx+2,...); phi (-3:nx+4,...); w_in, phi_convec_bc
+ *    (0:nx+1,0:ny+1); f_convec_bc,g_convec_bc (0:nx+1,0:ny+1,0:18).  The library copies, never
+ *    retains host pointers, and owns all device memory.
+ *  - one context per process per GPU, not thread safe (the reference issues all device work from one
+ *    host thread per rank, multiphase_3D/makefile:48).
+ *  - there is NO CPU fallback: every entry point fails with MFLBM_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MFLBM_H
+#define MFLBM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFLBM_OK 0
+#define MFLBM_ERR_ARG (-1)
+#define MFLBM_ERR_CUDA (-2)
+#define MFLBM_ERR_NCCL (-3)
+#define MFLBM_ERR_STATE (-4)
+
+#define MFLBM_SOLVER_SINGLEPHASE 0
+#define MFLBM_SOLVER_MULTIPHASE 1
+
+/* type(indirect_solid_boundary_nodes), MP/Module.F90:90-94 (gfortran/x86-64 layout, 96 bytes) */
+typedef struct {
+    int32_t ix, iy, iz, i_fluid_num;
+    int32_t neighbor_list[18];
+    double la_weight;
+} mflbm_solid_node;
+
+/* type(indirect_fluid_boundary_nodes), MP/Module.F90:98-101 (48 bytes) */
+typedef struct {
+    int32_t ix, iy, iz, pad_;
+    double nwx, nwy, nwz, theta;
+} mflbm_fluid_node;
+
+/* Everything the kernels read from the reference's module globals (MP/Module.F90). */
+typedef struct {
+    int32_t struct_size;            /* = sizeof(mflbm_config), ABI guard */
+    int32_t solver;                 /* MFLBM_SOLVER_* */
+    int32_t nx, ny, nz;             /* local slab (MP/Module.F90:80) */
+    int32_t nxGlobal, nyGlobal, nzGlobal;
+    int32_t idz, npz;               /* slab position; x,y undivided (MP/IO_multiphase.F90:495-498) */
+    int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference) */
+    int32_t domain_wall_status_z_min, domain_wall_status_z_max;
+    int32_t inlet_BC, outlet_BC;    /* 1 velocity / convective, 2 Zou-He pressure */
+    int32_t porous_plate_cmd, Z_porous_plate;
+    int32_t mrt;                    /* MP/preprocessor.h: 1..4, shipped value 2 */
+    int32_t iz_async;               /* MPI_async_layers_num z (>=4 for multiphase) */
+    int32_t num_solid_boundary, num_fluid_boundary;
+    int32_t device;                 /* CUDA ordinal; <0 = keep current (replaces setDevice, MP/Misc.F90:437) */
+    int32_t use_nccl;               /* 1: z-halo exchange between ranks with ncclSend/ncclRecv */
+    int32_t kernel_variant;         /* 0 = default (fused), 1 = reference-order dataflow (debug/parity) */
+    int32_t reserved_i[7];
+    double la_nui1, la_nui2;        /* 1/nu1, 1/nu2 (MP/Init_multiphase.F90:120-121) */
+    double gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
+    double s_e, s_e2, s_q, s_nu, s_pi, s_t; /* singlephase constant rates (SP/Initialization.F90:87-112) */
+    double reserved_d[8];
+    unsigned char nccl_unique_id[128];      /* from mflbm_nccl_unique_id on rank 0, broadcast by the caller */
+} mflbm_config;
+
+typedef struct mflbm_ctx mflbm_ctx;
+
+/* Host-array bundle for upload/download; NULL members are skipped. */
+typedef struct {
+    double *f[19];           /* f0..f18 */
+    double *g[19];           /* g0..g18 (multiphase) */
+    double *phi;             /* (-3:n+4)^3 */
+    double *phi_old;
+    double *cn_x, *cn_y, *cn_z, *c_norm; /* (-1:n+2)^3 ; download only */
+    double *curv;            /* (0:n+1)^3 ; download only */
+    double *u, *v, *w, *rho; /* (0:n+1)^3 ; download only (valid after mflbm_compute_macro_vars) */
+    int8_t *walls;           /* (-1:n+2)^3 ; upload only */
+    double *w_in;            /* (0:nx+1,0:ny+1) ; upload only */
+    double *f_convec_bc, *g_convec_bc, *phi_convec_bc;
+    const mflbm_solid_node *solid_boundary_nodes; /* upload only, cfg.num_solid_boundary entries */
+    const mflbm_fluid_node *fluid_boundary_nodes; /* upload only, cfg.num_fluid_boundary entries */
+} mflbm_arrays;
+
+/* "!$acc data" entry + setDevice: MP/Main_multiphase.F90:70,104-115 ; SP/Main.F90 */
+int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out);
+/* "!$acc end data": MP/Main_multiphase.F90:325 */
+void mflbm_destroy(mflbm_ctx *ctx);
+const char *mflbm_last_error(const mflbm_ctx *ctx);
+const char *mflbm_version(void);
+
+/* copy/copyin clauses of the data region (MP/Main_multiphase.F90:104-108); also used after
+ * initialization_old_multi (checkpoint restart, MP/Init_multiphase.F90:477-557) */
+int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *host);
+/* "!$acc update host(...)" in save_checkpoint / save_phi / save_macro / VTK_* (MP/IO_multiphase.F90:572,654,686,857) */
+int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *host);
+
+/* call main_iteration_kernel (MP/Main_multiphase.F90:167,341-486 ; SP/Main.F90:291-422):
+ * collision+streaming for this ntime parity, halo exchange, inlet/outlet/porous-plate BCs and
+ * (multiphase) color_gradient.  Asynchronous on the library's streams. */
+int mflbm_step(mflbm_ctx *ctx, int ntime);
+/* nsteps consecutive calls of mflbm_step starting at ntime0 (benchmark loop, MP/Main_multiphase.F90:515-531) */
+int mflbm_run(mflbm_ctx *ctx, int ntime0, int nsteps);
+/* call color_gradient (MP/Main_multiphase.F90:120 ; MP/Phase_gradient.F90:5-204) */
+int mflbm_color_gradient(mflbm_ctx *ctx);
+/* call compute_macro_vars (MP/Misc.F90:372-430 ; SP/Misc.F90:368-423) */
+int mflbm_compute_macro_vars(mflbm_ctx *ctx);
+
+/* device part of monitor (MP/Monitor.F90:27-107 ; SP/Monitor.F90:18-64): fills the reference's tk buffer.
+ * multiphase: tk[0:nz)=fl1, [nz:2nz)=fl2, vol1, vol2, mass1, mass2, pre, then umax, usq1, usq2 (7*nz+3)
+ * singlephase: tk[0:nz)=fl, [nz:2nz)=pre, then umax (2*nz+1).  Calls compute_macro_vars first. */
+int mflbm_monitor(mflbm_ctx *ctx, double *tk, int tk_len);
+/* cal_saturation partial sums v1,v2 of this slab (MP/Monitor.F90:527-538) */
+int mflbm_cal_saturation(mflbm_ctx *ctx, double *v1, double *v2);
+/* monitor_breakthrough count on plane nz-1 of the last slab (MP/Monitor.F90:483-495); 0 on other slabs */
+int mflbm_monitor_breakthrough(mflbm_ctx *ctx, int32_t *outlet_phase1_count);
+/* monitor_multiphase_steady_phasefield device part (MP/Monitor.F90:303-334): max u^2, max |phi-phi_old|, phi_old<-phi */
+int mflbm_monitor_steady_phasefield(mflbm_ctx *ctx, double *umax_sq, double *d_phi_max);
+/* monitor_multiphase_steady_capillarypressure device part (MP/Monitor.F90:383-423) */
+int mflbm_monitor_steady_capillarypressure(mflbm_ctx *ctx, double *umax_sq, double *pre_w, double *pre_nw,
+                                           int32_t *i_w, int32_t *i_nw);
+
+/* run-time changes of module scalars the driver makes between steps (force_z increments
+ * MP/Main_multiphase.F90, rho_in); name is the reference variable name */
+int mflbm_set_parameter(mflbm_ctx *ctx, const char *name, double value);
+
+/* "!$acc wait" / MPI_Barrier + system_clock of benchmark (MP/Main_multiphase.F90:524-538) */
+int mflbm_sync(mflbm_ctx *ctx);
+int mflbm_timer_start(mflbm_ctx *ctx);
+int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms); /* CUDA-event time on the compute stream */
+
+/* kernel launches issued by this context since create (bench.py "gpu_launches") */
+long long mflbm_launch_count(const mflbm_ctx *ctx);
+/* algorithmic device bytes held by the context */
+long long mflbm_device_bytes(const mflbm_ctx *ctx);
+
+/* NCCL bootstrap: rank 0 calls this and broadcasts the 128 bytes (MPI_Bcast in the Fortran driver,
+ * torch.distributed in bench.py); replaces MPI_CART_CREATE for the z ring (MP/Mpi_misc.F90:19-38) */
+int mflbm_nccl_unique_id(unsigned char id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,668 @@
+// mflbm_api.cu -- the extern "C" boundary declared in include/mflbm.h, the per-step schedule
+// (main_iteration_kernel, MP/Main_multiphase.F90:341-486 ; SP/Main.F90:291-422) and the NVLink z-halo
+// exchange that replaces the host-staged MPI of MP/Mpi.F90 / SP/Mpi.F90.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mflbm_internal.cuh"
+
+using namespace mflbm;
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen) so that single-GPU users and CPU-only symbol checks do not need it.
+// ---------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *h;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+
+static NcclApi *load_nccl(std::string &err) {
+    static NcclApi api;
+    static bool tried = false, ok = false;
+    if (tried) return ok ? &api : nullptr;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) break;
+    }
+    if (!api.h) {
+        err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+        return nullptr;
+    }
+#define SYM(field, name)                                     \
+    *(void **)(&api.field) = dlsym(api.h, name);             \
+    if (!api.field) {                                        \
+        err = std::string("NCCL symbol missing: ") + name;   \
+        return nullptr;                                      \
+    }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    ok = true;
+    return &api;
+}
+
+static thread_local std::string g_err;  // errors before a context exists
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char b_[512];                                                                               \
+            snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            if (ctx) ctx->err = b_;                                                                     \
+            g_err = b_;                                                                                 \
+            return MFLBM_ERR_CUDA;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+#define NC(call)                                                                                             \
+    do {                                                                                                     \
+        ncclResult_t r_ = (call);                                                                            \
+        if (r_ != ncclSuccess) {                                                                             \
+            char b_[512];                                                                                    \
+            snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ctx->nccl->GetErrorString(r_)); \
+            ctx->err = b_;                                                                                   \
+            return MFLBM_ERR_NCCL;                                                                           \
+        }                                                                                                    \
+    } while (0)
+
+static int fail(mflbm_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+
+template <typename T>
+static int dev_alloc(mflbm_ctx *ctx, T **p, size_t n, bool zero = true) {
+    void *q = nullptr;
+    CU(cudaMalloc(&q, n * sizeof(T)));
+    if (zero) CU(cudaMemset(q, 0, n * sizeof(T)));
+    ctx->allocs.push_back(q);
+    ctx->bytes += (long long)(n * sizeof(T));
+    *p = (T *)q;
+    return 0;
+}
+
+extern "C" const char *mflbm_version(void) { return "mflbm-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *mflbm_last_error(const mflbm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int mflbm_nccl_unique_id(unsigned char id[128]) {
+    std::string err;
+    NcclApi *api = load_nccl(err);
+    if (!api) return fail(nullptr, MFLBM_ERR_NCCL, err);
+    ncclUniqueId u;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (api->GetUniqueId(&u) != ncclSuccess) return fail(nullptr, MFLBM_ERR_NCCL, "ncclGetUniqueId failed");
+    memcpy(id, &u, 128);
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
+    mflbm_ctx *ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, MFLBM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int)sizeof(mflbm_config)) return fail(nullptr, MFLBM_ERR_ARG, "mflbm_config.struct_size mismatch");
+    if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 2) return fail(nullptr, MFLBM_ERR_ARG, "bad lattice dimensions");
+    if (cfg->npz < 1 || cfg->idz < 0 || cfg->idz >= cfg->npz) return fail(nullptr, MFLBM_ERR_ARG, "bad idz/npz");
+    if (cfg->jper != 0) return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) are not supported yet");
+    if (cfg->npz > 1 && !cfg->use_nccl) return fail(nullptr, MFLBM_ERR_ARG, "npz>1 requires use_nccl=1");
+    if (cfg->npz > 1 && cfg->solver == MFLBM_SOLVER_MULTIPHASE && cfg->iz_async < 4)
+        return fail(nullptr, MFLBM_ERR_ARG, "multiphase needs iz_async >= 4 (overlap_phi)");
+    if (cfg->npz > 1 && cfg->nz < 2 * (cfg->iz_async > 0 ? cfg->iz_async : 1))
+        return fail(nullptr, MFLBM_ERR_ARG, "nz_local must be >= 2*iz_async");
+    const long long sx = ((long long)cfg->nx + 8 + 15) / 16 * 16;
+    const long long sxy = sx * (cfg->ny + 8);
+    const long long ntot = 16 + sxy * (cfg->nz + 8) + 16;
+    if (ntot >= (1LL << 31)) return fail(nullptr, MFLBM_ERR_ARG, "slab too large for int32 cell indices");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, MFLBM_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    ctx = new mflbm_ctx();
+    ctx->cfg = *cfg;
+    ctx->bytes = 0;
+    ctx->launches = 0;
+    ctx->nccl = nullptr;
+    ctx->comm = nullptr;
+    ctx->macro_alloc = false;
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    ctx->red_dev = nullptr;
+    ctx->red_host = nullptr;
+    memset(&ctx->d, 0, sizeof(ctx->d));
+#define CREATE_FAIL(code)   \
+    do {                    \
+        g_err = ctx->err;   \
+        mflbm_destroy(ctx); \
+        return code;        \
+    } while (0)
+    if (cfg->device >= 0) {
+        if (cudaSetDevice(cfg->device) != cudaSuccess) {
+            ctx->err = "cudaSetDevice failed";
+            CREATE_FAIL(MFLBM_ERR_CUDA);
+        }
+    }
+    cudaGetDevice(&ctx->device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    if (prop.major < 10) {
+        ctx->err = "device is not sm_100-class; this library is built for sm_100a only";
+        CREATE_FAIL(MFLBM_ERR_CUDA);
+    }
+    int rc = [&]() -> int {
+        int lo, hi;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, lo));
+        CU(cudaStreamCreateWithPriority(&ctx->s_halo, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreate(&ctx->ev_t0));
+        CU(cudaEventCreate(&ctx->ev_t1));
+        CU(cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        Dev &d = ctx->d;
+        d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
+        d.g.sx = (int)sx; d.g.sxy = (int)sxy; d.g.base = 16; d.g.ntot = (int)ntot;
+        d.multiphase = cfg->solver == MFLBM_SOLVER_MULTIPHASE;
+        d.mrt = cfg->mrt;
+        d.la_nui1 = cfg->la_nui1; d.la_nui2 = cfg->la_nui2; d.gamma = cfg->gamma; d.beta = cfg->beta;
+        d.force_Z = cfg->force_Z; d.phi_inlet = cfg->phi_inlet; d.sa_inject = cfg->sa_inject;
+        d.relaxation = cfg->relaxation; d.uin_avg = cfg->uin_avg; d.rho_in = cfg->rho_in; d.rho_out = cfg->rho_out;
+        d.s_e = cfg->s_e; d.s_e2 = cfg->s_e2; d.s_q = cfg->s_q; d.s_nu = cfg->s_nu; d.s_pi = cfg->s_pi; d.s_t = cfg->s_t;
+        d.rk_weight2 = 1.0 / sqrt(2.0) / 36.0;
+        for (int q = 0; q < 19; q++) {
+            if (dev_alloc(ctx, &d.f[q], ntot)) return MFLBM_ERR_CUDA;
+            if (d.multiphase && dev_alloc(ctx, &d.gg[q], ntot)) return MFLBM_ERR_CUDA;
+        }
+        if (dev_alloc(ctx, &d.walls, ntot)) return MFLBM_ERR_CUDA;
+        if (dev_alloc(ctx, &d.w_in, (size_t)sxy + 32)) return MFLBM_ERR_CUDA;
+        if (dev_alloc(ctx, &d.f_convec, (size_t)19 * sxy + 32)) return MFLBM_ERR_CUDA;
+        if (d.multiphase) {
+            if (dev_alloc(ctx, &d.phi, ntot)) return MFLBM_ERR_CUDA;
+            if (dev_alloc(ctx, &d.cn_x, ntot) || dev_alloc(ctx, &d.cn_y, ntot) || dev_alloc(ctx, &d.cn_z, ntot) ||
+                dev_alloc(ctx, &d.c_norm, ntot) || dev_alloc(ctx, &d.curv, ntot))
+                return MFLBM_ERR_CUDA;
+            if (dev_alloc(ctx, &d.g_convec, (size_t)19 * sxy + 32)) return MFLBM_ERR_CUDA;
+            if (dev_alloc(ctx, &d.phi_convec, (size_t)sxy + 32)) return MFLBM_ERR_CUDA;
+            d.num_solid = cfg->num_solid_boundary;
+            d.num_fluid = cfg->num_fluid_boundary;
+            if (d.num_solid > 0) {
+                if (dev_alloc(ctx, &d.solid_cell, d.num_solid) || dev_alloc(ctx, &d.solid_mask, d.num_solid) ||
+                    dev_alloc(ctx, &d.solid_law, d.num_solid))
+                    return MFLBM_ERR_CUDA;
+            }
+            if (d.num_fluid > 0) {
+                if (dev_alloc(ctx, &d.fluid_cell, d.num_fluid) || dev_alloc(ctx, &d.fluid_nw, (size_t)5 * d.num_fluid))
+                    return MFLBM_ERR_CUDA;
+            }
+        }
+        ctx->red_len = 16 * (cfg->nz > cfg->ny ? cfg->nz : cfg->ny) + 64;
+        CU(cudaMalloc((void **)&ctx->red_dev, ctx->red_len * sizeof(double)));
+        CU(cudaMallocHost((void **)&ctx->red_host, ctx->red_len * sizeof(double)));
+        return 0;
+    }();
+    if (rc) CREATE_FAIL(rc);
+    ctx->open_z = (cfg->kper == 0 && cfg->domain_wall_status_z_min == 0 && cfg->domain_wall_status_z_max == 0);
+    ctx->peer_lo = (cfg->idz - 1 + cfg->npz) % cfg->npz;
+    ctx->peer_hi = (cfg->idz + 1) % cfg->npz;
+    if (cfg->use_nccl && cfg->npz > 1) {
+        ctx->nccl = load_nccl(ctx->err);
+        if (!ctx->nccl) CREATE_FAIL(MFLBM_ERR_NCCL);
+        ncclUniqueId u;
+        memcpy(&u, cfg->nccl_unique_id, 128);
+        ncclComm_t comm;
+        ncclResult_t r = ctx->nccl->CommInitRank(&comm, cfg->npz, u, cfg->idz);
+        if (r != ncclSuccess) {
+            ctx->err = std::string("ncclCommInitRank: ") + ctx->nccl->GetErrorString(r);
+            CREATE_FAIL(MFLBM_ERR_NCCL);
+        }
+        ctx->comm = comm;
+    }
+    *out = ctx;
+    return MFLBM_OK;
+}
+
+extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->red_dev) cudaFree(ctx->red_dev);
+    if (ctx->red_host) cudaFreeHost(ctx->red_host);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    delete ctx;
+}
+
+static int ensure_stage(mflbm_ctx *ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return 0;
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    CU(cudaMalloc((void **)&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return 0;
+}
+
+static int ensure_macro(mflbm_ctx *ctx) {
+    if (ctx->macro_alloc) return 0;
+    Dev &d = ctx->d;
+    if (dev_alloc(ctx, &d.u, d.g.ntot) || dev_alloc(ctx, &d.v, d.g.ntot) || dev_alloc(ctx, &d.w, d.g.ntot) ||
+        dev_alloc(ctx, &d.rho, d.g.ntot))
+        return MFLBM_ERR_CUDA;
+    ctx->macro_alloc = true;
+    return 0;
+}
+
+static int ensure_phi_old(mflbm_ctx *ctx) {
+    Dev &d = ctx->d;
+    if (d.phi_old) return 0;
+    if (dev_alloc(ctx, &d.phi_old, d.g.ntot)) return MFLBM_ERR_CUDA;
+    return 0;
+}
+
+// one field: host (ghost width o, nplanes planes starting at grid plane kbase) <-> device grid
+static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, int kbase, bool up) {
+    if (!host || !dev) return 0;
+    const Grid &g = ctx->d.g;
+    const size_t n = (size_t)(g.nx + 2 * o) * (g.ny + 2 * o) * nplanes;
+    if (ensure_stage(ctx, n * sizeof(double))) return MFLBM_ERR_CUDA;
+    if (up) {
+        CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
+        launch_repack(ctx, ctx->s_main, dev, ctx->stage, o, nplanes, kbase, true);
+        CU(cudaStreamSynchronize(ctx->s_main));
+    } else {
+        launch_repack(ctx, ctx->s_main, dev, ctx->stage, o, nplanes, kbase, false);
+        CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
+        CU(cudaStreamSynchronize(ctx->s_main));
+    }
+    return 0;
+}
+
+extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
+    if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    Dev &d = ctx->d;
+    const Grid &g = d.g;
+    const int nz = g.nz;
+    for (int q = 0; q < 19; q++) {
+        if (xfer(ctx, d.f[q], h->f[q], 1, nz + 2, 0, true)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer(ctx, d.gg[q], h->g[q], 1, nz + 2, 0, true)) return MFLBM_ERR_CUDA;
+    }
+    if (d.multiphase) {
+        if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, true)) return MFLBM_ERR_CUDA;
+        if (h->phi_old) {
+            if (ensure_phi_old(ctx)) return MFLBM_ERR_CUDA;
+            if (xfer(ctx, d.phi_old, h->phi_old, 4, nz + 8, -3, true)) return MFLBM_ERR_CUDA;
+        }
+        if (xfer(ctx, d.g_convec, h->g_convec_bc, 1, 19, -3, true)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, d.phi_convec, h->phi_convec_bc, 1, 1, -3, true)) return MFLBM_ERR_CUDA;
+    }
+    if (xfer(ctx, d.f_convec, h->f_convec_bc, 1, 19, -3, true)) return MFLBM_ERR_CUDA;
+    if (xfer(ctx, d.w_in, h->w_in, 1, 1, -3, true)) return MFLBM_ERR_CUDA;
+    if (h->walls) {
+        const size_t n = (size_t)(g.nx + 4) * (g.ny + 4) * (nz + 4);
+        if (ensure_stage(ctx, n)) return MFLBM_ERR_CUDA;
+        CU(cudaMemcpyAsync(ctx->stage, h->walls, n, cudaMemcpyHostToDevice, ctx->s_main));
+        // cells outside the (-1:n+2) box keep walls=0 like an untouched allocation would; they are never read
+        launch_repack_i8(ctx, ctx->s_main, d.walls, (int8_t *)ctx->stage, 2, true);
+        CU(cudaStreamSynchronize(ctx->s_main));
+    }
+    if (d.multiphase && h->solid_boundary_nodes && d.num_solid > 0) {
+        std::vector<int> cell(d.num_solid);
+        std::vector<unsigned> mask(d.num_solid);
+        std::vector<double> law(d.num_solid);
+        for (int n = 0; n < d.num_solid; n++) {
+            const mflbm_solid_node &s = h->solid_boundary_nodes[n];
+            if (s.ix < -2 || s.ix > g.nx + 3 || s.iy < -2 || s.iy > g.ny + 3 || s.iz < -2 || s.iz > nz + 3)
+                return fail(ctx, MFLBM_ERR_ARG, "solid boundary node outside the 3-ghost-layer box");
+            if (s.i_fluid_num < 0 || s.i_fluid_num > 18) return fail(ctx, MFLBM_ERR_ARG, "solid node: bad i_fluid_num");
+            cell[n] = g.cell(s.ix, s.iy, s.iz);
+            unsigned m = 0;
+            int prev = 0;
+            for (int t = 0; t < s.i_fluid_num; t++) {
+                const int e = s.neighbor_list[t];
+                if (e <= prev || e > 18) return fail(ctx, MFLBM_ERR_ARG, "solid node: neighbor_list must be increasing in 1..18");
+                m |= 1u << e;
+                prev = e;
+            }
+            if (s.ix >= 0 && s.ix <= g.nx + 1 && s.iy >= 0 && s.iy <= g.ny + 1 && s.iz >= 0 && s.iz <= nz + 1) m |= 0x80000000u;
+            mask[n] = m;
+            law[n] = s.la_weight;
+        }
+        CU(cudaMemcpy(d.solid_cell, cell.data(), cell.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.solid_mask, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.solid_law, law.data(), law.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (d.multiphase && h->fluid_boundary_nodes && d.num_fluid > 0) {
+        std::vector<int> cell(d.num_fluid);
+        std::vector<double> nw((size_t)5 * d.num_fluid);
+        for (int n = 0; n < d.num_fluid; n++) {
+            const mflbm_fluid_node &s = h->fluid_boundary_nodes[n];
+            if (s.ix < -1 || s.ix > g.nx + 2 || s.iy < -1 || s.iy > g.ny + 2 || s.iz < -1 || s.iz > nz + 2)
+                return fail(ctx, MFLBM_ERR_ARG, "fluid boundary node outside the 2-ghost-layer box");
+            cell[n] = g.cell(s.ix, s.iy, s.iz);
+            nw[5 * n + 0] = s.nwx; nw[5 * n + 1] = s.nwy; nw[5 * n + 2] = s.nwz;
+            nw[5 * n + 3] = cos(s.theta);  // dcos/dsin of MP/Phase_gradient.F90:238-242, evaluated once by the host libm
+            nw[5 * n + 4] = sin(s.theta);
+        }
+        CU(cudaMemcpy(d.fluid_cell, cell.data(), cell.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.fluid_nw, nw.data(), nw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
+    if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    Dev &d = ctx->d;
+    const int nz = d.g.nz;
+    CU(cudaStreamSynchronize(ctx->s_main));
+    for (int q = 0; q < 19; q++) {
+        if (xfer(ctx, d.f[q], h->f[q], 1, nz + 2, 0, false)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer(ctx, d.gg[q], h->g[q], 1, nz + 2, 0, false)) return MFLBM_ERR_CUDA;
+    }
+    if (d.multiphase) {
+        if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, false)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, d.phi_old, h->phi_old, 4, nz + 8, -3, false)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, d.cn_x, h->cn_x, 2, nz + 4, -1, false) || xfer(ctx, d.cn_y, h->cn_y, 2, nz + 4, -1, false) ||
+            xfer(ctx, d.cn_z, h->cn_z, 2, nz + 4, -1, false) || xfer(ctx, d.c_norm, h->c_norm, 2, nz + 4, -1, false) ||
+            xfer(ctx, d.curv, h->curv, 1, nz + 2, 0, false))
+            return MFLBM_ERR_CUDA;
+        if (xfer(ctx, d.g_convec, h->g_convec_bc, 1, 19, -3, false)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, d.phi_convec, h->phi_convec_bc, 1, 1, -3, false)) return MFLBM_ERR_CUDA;
+    }
+    if (xfer(ctx, d.f_convec, h->f_convec_bc, 1, 19, -3, false)) return MFLBM_ERR_CUDA;
+    if (h->u || h->v || h->w || h->rho) {
+        if (!ctx->macro_alloc) return fail(ctx, MFLBM_ERR_STATE, "u,v,w,rho requested before mflbm_compute_macro_vars");
+        if (xfer(ctx, d.u, h->u, 1, nz + 2, 0, false) || xfer(ctx, d.v, h->v, 1, nz + 2, 0, false) ||
+            xfer(ctx, d.w, h->w, 1, nz + 2, 0, false) || xfer(ctx, d.rho, h->rho, 1, nz + 2, 0, false))
+            return MFLBM_ERR_CUDA;
+    }
+    return MFLBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z-halo exchange between slabs over NVLink (NCCL p2p).  Whole padded planes are contiguous in the
+// SoA grid, so they are sent in place: no pack/unpack kernels (the reference's MP/Mpi.F90:116-146,
+// :239-269, :374-396, :497-519 degenerate to address arithmetic).  Plane pairs follow the reference:
+//   pull (after an even step): own k=1 {6,14,13,18,17} -> lower neighbour's k=nz+1 ; own k=nz {5,11,12,15,16} -> upper k=0
+//   push (after an odd step):  own k=0 {5,11,12,15,16} -> lower neighbour's k=nz   ; own k=nz+1 {6,14,13,18,17} -> upper k=1
+//   phi: own 1..4 -> lower's nz+1..nz+4 ; own nz-3..nz -> upper's -3..0 (MP/Mpi.F90:624-631, :702-727)
+// The wrap between the first and last slab is skipped on a non-periodic domain.
+// ---------------------------------------------------------------------------------------------------
+static int halo_exchange(mflbm_ctx *ctx, cudaStream_t st, bool push) {
+    const Dev &d = ctx->d;
+    const Grid &g = d.g;
+    const mflbm_config &cfg = ctx->cfg;
+    const int nz = g.nz;
+    const bool has_lo = cfg.kper == 1 || cfg.idz != 0;
+    const bool has_hi = cfg.kper == 1 || cfg.idz != cfg.npz - 1;
+    static const int qM[5] = {6, 14, 13, 18, 17}, qP[5] = {5, 11, 12, 15, 16};
+    const size_t n = (size_t)g.sxy;
+    NC(ctx->nccl->GroupStart());
+    for (int fl = 0; fl < (d.multiphase ? 2 : 1); fl++) {
+        double *const *F = fl == 0 ? d.f : d.gg;
+        for (int m = 0; m < 5; m++) {
+            if (!push) {
+                if (has_lo) {
+                    NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(1), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+                    NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(0), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+                }
+                if (has_hi) {
+                    NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+                    NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+                }
+            } else {
+                if (has_lo) {
+                    NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(0), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+                    NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(1), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+                }
+                if (has_hi) {
+                    NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+                    NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+                }
+            }
+        }
+    }
+    if (d.multiphase) {
+        if (has_lo) {
+            NC(ctx->nccl->Send(d.phi + g.plane_begin(1), 4 * n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+            NC(ctx->nccl->Recv(d.phi + g.plane_begin(-3), 4 * n, ncclDouble, ctx->peer_lo, ctx->comm, st));
+        }
+        if (has_hi) {
+            NC(ctx->nccl->Send(d.phi + g.plane_begin(nz - 3), 4 * n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+            NC(ctx->nccl->Recv(d.phi + g.plane_begin(nz + 1), 4 * n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+        }
+    }
+    NC(ctx->nccl->GroupEnd());
+    return 0;
+}
+
+static int check_launch(mflbm_ctx *ctx) {
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// main_iteration_kernel for one ntime
+static int step_impl(mflbm_ctx *ctx, int ntime) {
+    const mflbm_config &cfg = ctx->cfg;
+    const int nz = cfg.nz;
+    const bool odd = (ntime % 2) != 0;
+    cudaStream_t s = ctx->s_main;
+    if (ctx->comm) {
+        // boundary slabs first, exchange on the high-priority halo stream while the interior runs
+        // (MP/Main_multiphase.F90:358-387, :423-458)
+        const int iz = cfg.iz_async > 0 ? cfg.iz_async : 1;
+        launch_collide(ctx, s, odd, 1, iz);
+        launch_collide(ctx, s, odd, nz - iz + 1, nz);
+        CU(cudaEventRecord(ctx->ev_slab, s));
+        CU(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_slab, 0));
+        if (halo_exchange(ctx, ctx->s_halo, odd)) return MFLBM_ERR_NCCL;
+        CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
+        launch_collide(ctx, s, odd, iz + 1, nz - iz);
+        CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
+    } else {
+        launch_collide(ctx, s, odd, 1, nz);
+        if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
+    }
+    launch_bc(ctx, s, odd);
+    launch_color_gradient(ctx, s);
+    return check_launch(ctx);
+}
+
+extern "C" int mflbm_step(mflbm_ctx *ctx, int ntime) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    return step_impl(ctx, ntime);
+}
+
+extern "C" int mflbm_run(mflbm_ctx *ctx, int ntime0, int nsteps) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    for (int n = 0; n < nsteps; n++) {
+        const int rc = step_impl(ctx, ntime0 + n);
+        if (rc) return rc;
+    }
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_color_gradient(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    launch_color_gradient(ctx, ctx->s_main);
+    return check_launch(ctx);
+}
+
+extern "C" int mflbm_compute_macro_vars(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (ensure_macro(ctx)) return MFLBM_ERR_CUDA;
+    launch_macro(ctx, ctx->s_main);
+    return check_launch(ctx);
+}
+
+static int fetch_red(mflbm_ctx *ctx, int n) {
+    CU(cudaMemcpyAsync(ctx->red_host, ctx->red_dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
+    CU(cudaStreamSynchronize(ctx->s_main));
+    return 0;
+}
+
+extern "C" int mflbm_monitor(mflbm_ctx *ctx, double *tk, int tk_len) {
+    if (!ctx || !tk) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    const int nz = ctx->cfg.nz;
+    const bool mp = ctx->d.multiphase;
+    const int need = mp ? 7 * nz + 3 : 2 * nz + 1;
+    if (tk_len < need) return fail(ctx, MFLBM_ERR_ARG, "tk buffer too small (MP/Init_multiphase.F90:799: 7*nz+3)");
+    int rc = mflbm_compute_macro_vars(ctx);
+    if (rc) return rc;
+    launch_monitor(ctx, ctx->s_main, ctx->red_dev);
+    if (check_launch(ctx) || fetch_red(ctx, 10 * nz)) return MFLBM_ERR_CUDA;
+    const double *r = ctx->red_host;
+    double umax = 0, usq1 = 0, usq2 = 0;
+    for (int k = 0; k < nz; k++) {
+        if (umax < r[7 * nz + k]) umax = r[7 * nz + k];
+        usq1 += r[8 * nz + k];
+        usq2 += r[9 * nz + k];
+    }
+    if (mp) {
+        memcpy(tk, r, 7 * nz * sizeof(double));
+        tk[7 * nz] = umax; tk[7 * nz + 1] = usq1; tk[7 * nz + 2] = usq2;
+    } else {
+        memcpy(tk, r, nz * sizeof(double));               // fl
+        memcpy(tk + nz, r + 6 * nz, nz * sizeof(double)); // pre
+        tk[2 * nz] = umax;
+    }
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_cal_saturation(mflbm_ctx *ctx, double *v1, double *v2) {
+    if (!ctx || !v1 || !v2) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
+    CU(cudaSetDevice(ctx->device));
+    const int nz = ctx->cfg.nz;
+    launch_saturation(ctx, ctx->s_main, ctx->red_dev);
+    if (check_launch(ctx) || fetch_red(ctx, 2 * nz)) return MFLBM_ERR_CUDA;
+    double a = 0, b = 0;
+    for (int k = 0; k < nz; k++) { a += ctx->red_host[k]; b += ctx->red_host[nz + k]; }
+    *v1 = a; *v2 = b;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_monitor_breakthrough(mflbm_ctx *ctx, int32_t *count) {
+    if (!ctx || !count) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
+    CU(cudaSetDevice(ctx->device));
+    *count = 0;
+    if (ctx->cfg.idz != ctx->cfg.npz - 1) return MFLBM_OK;
+    const int ny = ctx->cfg.ny;
+    launch_breakthrough(ctx, ctx->s_main, ctx->red_dev);
+    if (check_launch(ctx) || fetch_red(ctx, ny)) return MFLBM_ERR_CUDA;
+    long long t = 0;
+    for (int j = 0; j < ny; j++) t += (long long)ctx->red_host[j];
+    *count = (int32_t)t;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_monitor_steady_phasefield(mflbm_ctx *ctx, double *umax_sq, double *d_phi_max) {
+    if (!ctx || !umax_sq || !d_phi_max) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
+    if (ensure_phi_old(ctx)) return MFLBM_ERR_CUDA;
+    int rc = mflbm_compute_macro_vars(ctx);
+    if (rc) return rc;
+    const int nz = ctx->cfg.nz;
+    launch_steady_phasefield(ctx, ctx->s_main, ctx->red_dev);
+    if (check_launch(ctx) || fetch_red(ctx, 2 * nz)) return MFLBM_ERR_CUDA;
+    double a = 0, b = 0;
+    for (int k = 0; k < nz; k++) {
+        if (a < ctx->red_host[k]) a = ctx->red_host[k];
+        if (b < ctx->red_host[nz + k]) b = ctx->red_host[nz + k];
+    }
+    *umax_sq = a; *d_phi_max = b;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_monitor_steady_capillarypressure(mflbm_ctx *ctx, double *umax_sq, double *pre_w, double *pre_nw,
+                                                      int32_t *i_w, int32_t *i_nw) {
+    if (!ctx || !umax_sq || !pre_w || !pre_nw || !i_w || !i_nw) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
+    int rc = mflbm_compute_macro_vars(ctx);
+    if (rc) return rc;
+    const int nz = ctx->cfg.nz;
+    launch_steady_cappres(ctx, ctx->s_main, ctx->red_dev);
+    if (check_launch(ctx) || fetch_red(ctx, 5 * nz)) return MFLBM_ERR_CUDA;
+    const double *r = ctx->red_host;
+    double um = 0, pw = 0, pnw = 0;
+    long long cw = 0, cnw = 0;
+    for (int k = 0; k < nz; k++) {
+        if (um < r[k]) um = r[k];
+        pw += r[nz + k]; pnw += r[2 * nz + k];
+        cw += (long long)r[3 * nz + k]; cnw += (long long)r[4 * nz + k];
+    }
+    *umax_sq = um; *pre_w = pw; *pre_nw = pnw; *i_w = (int32_t)cw; *i_nw = (int32_t)cnw;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_set_parameter(mflbm_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    Dev &d = ctx->d;
+    if (!strcmp(name, "force_Z") || !strcmp(name, "force_z")) d.force_Z = value;
+    else if (!strcmp(name, "rho_in")) d.rho_in = value;
+    else if (!strcmp(name, "rho_out")) d.rho_out = value;
+    else if (!strcmp(name, "uin_avg")) d.uin_avg = value;
+    else if (!strcmp(name, "phi_inlet")) d.phi_inlet = value;
+    else if (!strcmp(name, "sa_inject")) d.sa_inject = value;
+    else if (!strcmp(name, "relaxation")) d.relaxation = value;
+    else return fail(ctx, MFLBM_ERR_ARG, std::string("unknown parameter ") + name);
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_sync(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->s_halo));
+    CU(cudaStreamSynchronize(ctx->s_main));
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_timer_start(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaEventRecord(ctx->ev_t0, ctx->s_main));
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms) {
+    if (!ctx || !elapsed_ms) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaEventRecord(ctx->ev_t1, ctx->s_main));
+    CU(cudaEventSynchronize(ctx->ev_t1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    *elapsed_ms = ms;
+    return MFLBM_OK;
+}
+
+extern "C" long long mflbm_launch_count(const mflbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long mflbm_device_bytes(const mflbm_ctx *ctx) { return ctx ? ctx->bytes : 0; }

@@ -1,0 +1,121 @@
+// mflbm_internal.cuh -- device-side layout, parameter block and context of the MF-LBM hot path.
+//
+// HBM layout (DESIGN.md "Data layout"): every 3-D field lives on ONE padded grid so that a single
+// linear cell index addresses all arrays:
+//     cell(i,j,k) = base + (i-1) + sx*(j+3) + sxy*(k+3),   i in [-3,nx+4], j in [-3,ny+4], k in [-3,nz+4]
+// with sx = round_up(nx+8,16) doubles (rows start 128-byte aligned at i=1; the 4 low-x ghosts of a row
+// sit in the tail padding of the previous row), sxy = sx*(ny+8), base = 16.
+// Structure of arrays: one such grid per population (f0..f18, g0..g18), phi, and the optional
+// derived fields.  int32 cell indices are sufficient for one GPU (<= 2^31 cells is checked at create).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mflbm.h"
+
+namespace mflbm {
+
+// D3Q19 lattice of the reference, MP/Module.F90:111-114
+__host__ __device__ constexpr int EX(int q) {
+    constexpr int t[19] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+    return t[q];
+}
+__host__ __device__ constexpr int EY(int q) {
+    constexpr int t[19] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+    return t[q];
+}
+__host__ __device__ constexpr int EZ(int q) {
+    constexpr int t[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+    return t[q];
+}
+__host__ __device__ constexpr int OPC(int q) {
+    constexpr int t[19] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+    return t[q];
+}
+
+struct Grid {
+    int nx, ny, nz;
+    int sx;    // x stride (doubles), multiple of 16
+    int sxy;   // sx*(ny+8)
+    int base;  // 16
+    int ntot;  // allocated cells per field
+    __host__ __device__ __forceinline__ int cell(int i, int j, int k) const { return base + (i - 1) + sx * (j + 3) + sxy * (k + 3); }
+    __host__ __device__ __forceinline__ int off(int q) const { return EX(q) + sx * EY(q) + sxy * EZ(q); }
+    __host__ __device__ __forceinline__ int cell2(int i, int j) const { return base + (i - 1) + sx * (j + 3); }  // 2-D plane fields
+    int plane_cells() const { return sxy; }
+    // first cell of the contiguous storage of plane k (includes the row paddings): cell(-3,-3,k)
+    __host__ __device__ __forceinline__ int plane_begin(int k) const { return base - 4 + sxy * (k + 3); }
+};
+
+// Kernel parameter block (by value; < 4 KB)
+struct Dev {
+    Grid g;
+    double *f[19];
+    double *gg[19];  // g0..g18 (fluid 2)
+    double *phi, *phi_old;
+    double *cn_x, *cn_y, *cn_z, *c_norm, *curv;
+    double *u, *v, *w, *rho;
+    int8_t *walls;
+    double *w_in, *f_convec, *g_convec, *phi_convec;  // plane fields; *_convec hold 19 planes of sx*(ny+8)
+    // solid / fluid boundary node lists (device SoA, built at upload)
+    int *solid_cell;
+    unsigned *solid_mask;  // bits 1..18: fluid neighbour e_n present (list order == increasing n); bit 31: inside 0..n+1 box
+    double *solid_law;     // la_weight
+    int num_solid;
+    int *fluid_cell;
+    double *fluid_nw;  // 5 doubles per node: nwx,nwy,nwz,cos(theta),sin(theta)
+    int num_fluid;
+    // scalars
+    int multiphase, mrt;
+    double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
+    double s_e, s_e2, s_q, s_nu, s_pi, s_t;
+    double rk_weight2;  // 1/sqrt(2)/36 evaluated on the host like MP/Module.F90:225
+};
+
+}  // namespace mflbm
+
+struct ncclComm;
+struct NcclApi;
+
+struct mflbm_ctx {
+    mflbm_config cfg;
+    mflbm::Dev d;
+    int device;
+    cudaStream_t s_main, s_halo;
+    cudaEvent_t ev_t0, ev_t1, ev_slab, ev_halo, ev_fork;
+    std::vector<void *> allocs;
+    long long bytes;
+    long long launches;
+    std::string err;
+    // reduction scratch
+    double *red_dev;   // device
+    double *red_host;  // pinned
+    int red_len;
+    // staging buffer for layout conversion on upload/download
+    double *stage;
+    size_t stage_bytes;
+    // NCCL
+    NcclApi *nccl;
+    ncclComm *comm;
+    int peer_lo, peer_hi;  // ranks of z-1 / z+1 neighbours (periodic ring)
+    bool open_z;
+    bool macro_alloc;
+};
+
+namespace mflbm {
+// launchers implemented in the .cu files
+void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1);
+void launch_color_gradient(mflbm_ctx *c, cudaStream_t st);
+void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
+void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
+void launch_macro(mflbm_ctx *c, cudaStream_t st);
+void launch_monitor(mflbm_ctx *c, cudaStream_t st, double *out /*device, (10)*nz*/);
+void launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out /*device, 2*nz*/);
+void launch_breakthrough(mflbm_ctx *c, cudaStream_t st, double *out);
+void launch_steady_phasefield(mflbm_ctx *c, cudaStream_t st, double *out /*2*nz*/);
+void launch_steady_cappres(mflbm_ctx *c, cudaStream_t st, double *out /*5*nz*/);
+void launch_repack(mflbm_ctx *c, cudaStream_t st, double *grid, double *packed, int ghost, int nplanes_z, int kbase, bool to_grid);
+void launch_repack_i8(mflbm_ctx *c, cudaStream_t st, int8_t *grid, int8_t *packed, int ghost, bool to_grid);
+}  // namespace mflbm

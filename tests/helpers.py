@@ -1,0 +1,83 @@
+"""Shared test plumbing: build an oracle case and the matching GPU context through the C ABI."""
+import numpy as np
+
+import mflbm_b200 as M
+from oracle.oracle import Oracle, default_params
+
+PDF_NAMES = ["f", "g"]
+
+
+def make_oracle(**kw):
+    walls_global = kw.pop("walls_global", None)
+    p = default_params(**kw)
+    o = Oracle(p)
+    o.setup(walls_global)
+    return o
+
+
+def ctx_from_oracle(o, strict=False, **over):
+    """mflbm_create + mflbm_upload from the oracle's state (what the Fortran driver would hand over)."""
+    p = o.p
+    mp = bool(p.multiphase)
+    solid = o.solid_nodes() if mp else np.zeros(0, M.SOLID_DTYPE)
+    fluid = o.fluid_nodes() if mp else np.zeros(0, M.FLUID_DTYPE)
+    cfg = dict(solver=1 if mp else 0, nx=o.nx, ny=o.ny, nz=o.nz, nxGlobal=p.nxG, nyGlobal=p.nyG, nzGlobal=p.nzG,
+               idz=p.idz, npz=p.npz, jper=p.jper, kper=p.kper, domain_wall_status_z_min=p.wsz0,
+               domain_wall_status_z_max=p.wsz1, inlet_BC=p.inlet_BC, outlet_BC=p.outlet_BC,
+               porous_plate_cmd=p.porous_plate_cmd, Z_porous_plate=p.Z_porous_plate, mrt=p.mrt, iz_async=4,
+               num_solid_boundary=len(solid), num_fluid_boundary=len(fluid),
+               la_nui1=o.get_double("la_nui1"), la_nui2=o.get_double("la_nui2"), gamma=p.gamma, beta=p.beta,
+               force_Z=o.get_double("force_Z"), phi_inlet=o.get_double("phi_inlet"), sa_inject=p.sa_inject,
+               relaxation=o.get_double("relaxation"), uin_avg=o.get_double("uin_avg"), rho_in=o.get_double("rho_in"),
+               rho_out=o.get_double("rho_out"), s_e=o.get_double("s_e"), s_e2=o.get_double("s_e2"),
+               s_q=o.get_double("s_q"), s_nu=o.get_double("s_nu"), s_pi=o.get_double("s_pi"), s_t=o.get_double("s_t"))
+    cfg.update(over)
+    ctx = M.Context(strict=strict, **cfg)
+    upload_from_oracle(ctx, o)
+    return ctx
+
+
+def upload_from_oracle(ctx, o):
+    mp = o.mp
+    arrays = dict(f=[o.f(q) for q in range(19)], walls=o.walls, w_in=o.field("w_in"), f_convec_bc=o.field("f_convec_bc"))
+    if mp:
+        arrays.update(g=[o.g(q) for q in range(19)], phi=o.field("phi"), g_convec_bc=o.field("g_convec_bc"),
+                      phi_convec_bc=o.field("phi_convec_bc"), solid_boundary_nodes=o.solid_nodes(),
+                      fluid_boundary_nodes=o.fluid_nodes())
+    ctx.upload(**arrays)
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|) -- field-level relative error (the populations span many decades)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    scale = np.max(np.abs(b))
+    if scale == 0:
+        return float(np.max(np.abs(a)))
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def compare_state(ctx, o, tol, fields=("phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv"), interior_only=False):
+    """Compare all populations (+ fields) of the GPU context with the oracle.  Returns the worst error."""
+    names = ["f"] + (["g"] if o.mp else [])
+    names += [n for n in fields if o.mp]
+    got = ctx.download(*names)
+    worst = 0.0
+    report = {}
+    for q in range(19):
+        e = rel_err(got["f"][q], o.f(q))
+        report["f%d" % q] = e
+        if o.mp:
+            e2 = rel_err(got["g"][q], o.g(q))
+            report["g%d" % q] = e2
+    if o.mp:
+        for n in fields:
+            a, b = got[n], o.field(n)
+            if n == "phi":
+                # phi in x/y/z ghost cells outside 1..n that neither side ever writes is identical (uploaded)
+                pass
+            report[n] = rel_err(a, b)
+    worst = max(report.values())
+    bad = {k: v for k, v in report.items() if not (v <= tol)}
+    assert not bad, "fields beyond tol %g: %s" % (tol, bad)
+    return worst

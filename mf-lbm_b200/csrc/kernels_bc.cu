@@ -14,6 +14,12 @@ namespace mflbm {
 #define C13 0.333333333333333333
 #define C16 0.166666666666666667
 
+// population index of dense cell c: identity on the dense layout, active-node index on the sparse layout.
+// Every cell touched for a column whose boundary node is fluid is a D3Q19 neighbour of that fluid node,
+// hence active; columns whose boundary node is solid are skipped on the sparse layout (the reference's
+// blend new*(1-w)+old*w leaves them unchanged).
+#define X(c) (P.sparse ? P.smap[(c)] : (c))
+
 __device__ __forceinline__ void phi_inlet_ghost(const Dev &P, int i, int j, int wi) {
     const int c0 = P.g.cell(i, j, 0);
     const double v = P.phi_inlet * (1 - wi) + P.phi[c0] * wi;
@@ -31,6 +37,7 @@ __global__ void k_inlet_velocity(const Dev P) {
     const int c0 = P.g.cell(i, j, 0), c1 = P.g.cell(i, j, 1);
     const int wi = P.walls[c1];
     if (MP) phi_inlet_ghost(P, i, j, wi);
+    if (P.sparse && wi) return;
     double tmp2 = P.w_in[P.g.cell2(i, j)] * P.relaxation;
     const double tmp1 = MP ? tmp2 * P.sa_inject : tmp2;
     tmp2 = tmp2 - tmp1;
@@ -39,17 +46,17 @@ __global__ void k_inlet_velocity(const Dev P) {
         double *const *F = fl == 0 ? P.f : P.gg;
         const double t = fl == 0 ? tmp1 : tmp2;
         if (!AFTER) {
-            F[5][c0] = (F[6][c1] + 6.0 * W1 * t) * (1 - wi) + F[5][c0] * wi;
-            F[11][c0 - 1] = (F[14][c1] + 6.0 * W2 * t) * (1 - wi) + F[11][c0 - 1] * wi;
-            F[12][c0 + 1] = (F[13][c1] + 6.0 * W2 * t) * (1 - wi) + F[12][c0 + 1] * wi;
-            F[15][c0 - sx] = (F[18][c1] + 6.0 * W2 * t) * (1 - wi) + F[15][c0 - sx] * wi;
-            F[16][c0 + sx] = (F[17][c1] + 6.0 * W2 * t) * (1 - wi) + F[16][c0 + sx] * wi;
+            F[5][X(c0)] = (F[6][X(c1)] + 6.0 * W1 * t) * (1 - wi) + F[5][X(c0)] * wi;
+            F[11][X(c0 - 1)] = (F[14][X(c1)] + 6.0 * W2 * t) * (1 - wi) + F[11][X(c0 - 1)] * wi;
+            F[12][X(c0 + 1)] = (F[13][X(c1)] + 6.0 * W2 * t) * (1 - wi) + F[12][X(c0 + 1)] * wi;
+            F[15][X(c0 - sx)] = (F[18][X(c1)] + 6.0 * W2 * t) * (1 - wi) + F[15][X(c0 - sx)] * wi;
+            F[16][X(c0 + sx)] = (F[17][X(c1)] + 6.0 * W2 * t) * (1 - wi) + F[16][X(c0 + sx)] * wi;
         } else {
-            F[6][c1] = (F[5][c0] + 6.0 * W1 * t) * (1 - wi) + F[6][c1] * wi;
-            F[13][c1] = (F[12][c0 + 1] + 6.0 * W2 * t) * (1 - wi) + F[13][c1] * wi;
-            F[14][c1] = (F[11][c0 - 1] + 6.0 * W2 * t) * (1 - wi) + F[14][c1] * wi;
-            F[17][c1] = (F[16][c0 + sx] + 6.0 * W2 * t) * (1 - wi) + F[17][c1] * wi;
-            F[18][c1] = (F[15][c0 - sx] + 6.0 * W2 * t) * (1 - wi) + F[18][c1] * wi;
+            F[6][X(c1)] = (F[5][X(c0)] + 6.0 * W1 * t) * (1 - wi) + F[6][X(c1)] * wi;
+            F[13][X(c1)] = (F[12][X(c0 + 1)] + 6.0 * W2 * t) * (1 - wi) + F[13][X(c1)] * wi;
+            F[14][X(c1)] = (F[11][X(c0 - 1)] + 6.0 * W2 * t) * (1 - wi) + F[14][X(c1)] * wi;
+            F[17][X(c1)] = (F[16][X(c0 + sx)] + 6.0 * W2 * t) * (1 - wi) + F[17][X(c1)] * wi;
+            F[18][X(c1)] = (F[15][X(c0 - sx)] + 6.0 * W2 * t) * (1 - wi) + F[18][X(c1)] * wi;
         }
     }
 }
@@ -62,6 +69,7 @@ __global__ void k_inlet_pressure(const Dev P) {
     const int c0 = P.g.cell(i, j, 0), c1 = c0 + sxy, c2 = c1 + sxy;
     const int wi = P.walls[c1];
     if (MP) phi_inlet_ghost(P, i, j, wi);
+    if (P.sparse && wi) return;
     double r2 = P.rho_in;
     const double r1 = MP ? P.rho_in * P.sa_inject : P.rho_in;
     r2 = r2 - r1;
@@ -70,29 +78,29 @@ __global__ void k_inlet_pressure(const Dev P) {
         double *const *F = fl == 0 ? P.f : P.gg;
         const double rin = fl == 0 ? r1 : r2;
         if (!AFTER) {
-            const double t = (rin - (F[0][c1] + F[1][c1 - 1] + F[2][c1 + 1] + F[3][c1 - sx] + F[4][c1 + sx] + F[7][c1 - 1 - sx] +
-                                     F[8][c1 + 1 - sx] + F[9][c1 - 1 + sx] + F[10][c1 + 1 + sx] +
-                                     2.0 * (F[6][c2] + F[14][c2 + 1] + F[13][c2 - 1] + F[18][c2 + sx] + F[17][c2 - sx]))) *
+            const double t = (rin - (F[0][X(c1)] + F[1][X(c1 - 1)] + F[2][X(c1 + 1)] + F[3][X(c1 - sx)] + F[4][X(c1 + sx)] + F[7][X(c1 - 1 - sx)] +
+                                     F[8][X(c1 + 1 - sx)] + F[9][X(c1 - 1 + sx)] + F[10][X(c1 + 1 + sx)] +
+                                     2.0 * (F[6][X(c2)] + F[14][X(c2 + 1)] + F[13][X(c2 - 1)] + F[18][X(c2 + sx)] + F[17][X(c2 - sx)]))) *
                              P.relaxation;
-            const double tnx = 0.5 * (F[1][c1 - 1] + F[7][c1 - 1 - sx] + F[9][c1 - 1 + sx] - (F[2][c1 + 1] + F[8][c1 + 1 - sx] + F[10][c1 + 1 + sx]));
-            const double tny = 0.5 * (F[3][c1 - sx] + F[7][c1 - 1 - sx] + F[8][c1 + 1 - sx] - (F[4][c1 + sx] + F[10][c1 + 1 + sx] + F[9][c1 - 1 + sx]));
-            F[5][c0] = (F[6][c2] + C13 * t) * (1 - wi) + F[5][c0] * wi;
-            F[11][c0 - 1] = (F[14][c2 + 1] + C16 * t - tnx) * (1 - wi) + F[11][c0 - 1] * wi;
-            F[12][c0 + 1] = (F[13][c2 - 1] + C16 * t + tnx) * (1 - wi) + F[12][c0 + 1] * wi;
-            F[15][c0 - sx] = (F[18][c2 + sx] + C16 * t - tny) * (1 - wi) + F[15][c0 - sx] * wi;
-            F[16][c0 + sx] = (F[17][c2 - sx] + C16 * t + tny) * (1 - wi) + F[16][c0 + sx] * wi;
+            const double tnx = 0.5 * (F[1][X(c1 - 1)] + F[7][X(c1 - 1 - sx)] + F[9][X(c1 - 1 + sx)] - (F[2][X(c1 + 1)] + F[8][X(c1 + 1 - sx)] + F[10][X(c1 + 1 + sx)]));
+            const double tny = 0.5 * (F[3][X(c1 - sx)] + F[7][X(c1 - 1 - sx)] + F[8][X(c1 + 1 - sx)] - (F[4][X(c1 + sx)] + F[10][X(c1 + 1 + sx)] + F[9][X(c1 - 1 + sx)]));
+            F[5][X(c0)] = (F[6][X(c2)] + C13 * t) * (1 - wi) + F[5][X(c0)] * wi;
+            F[11][X(c0 - 1)] = (F[14][X(c2 + 1)] + C16 * t - tnx) * (1 - wi) + F[11][X(c0 - 1)] * wi;
+            F[12][X(c0 + 1)] = (F[13][X(c2 - 1)] + C16 * t + tnx) * (1 - wi) + F[12][X(c0 + 1)] * wi;
+            F[15][X(c0 - sx)] = (F[18][X(c2 + sx)] + C16 * t - tny) * (1 - wi) + F[15][X(c0 - sx)] * wi;
+            F[16][X(c0 + sx)] = (F[17][X(c2 - sx)] + C16 * t + tny) * (1 - wi) + F[16][X(c0 + sx)] * wi;
         } else {
-            const double t = (rin - (F[0][c1] + F[2][c1] + F[1][c1] + F[4][c1] + F[3][c1] + F[8][c1] + F[7][c1] + F[10][c1] + F[9][c1] +
-                                     2.0 * (F[5][c1] + F[11][c1] + F[12][c1] + F[15][c1] + F[16][c1]))) *
+            const double t = (rin - (F[0][X(c1)] + F[2][X(c1)] + F[1][X(c1)] + F[4][X(c1)] + F[3][X(c1)] + F[8][X(c1)] + F[7][X(c1)] + F[10][X(c1)] + F[9][X(c1)] +
+                                     2.0 * (F[5][X(c1)] + F[11][X(c1)] + F[12][X(c1)] + F[15][X(c1)] + F[16][X(c1)]))) *
                              P.relaxation;
-            const double tnx = 0.5 * (F[2][c1] + F[8][c1] + F[10][c1] - (F[1][c1] + F[7][c1] + F[9][c1]));
-            const double tny = 0.5 * (F[4][c1] + F[9][c1] + F[10][c1] - (F[3][c1] + F[8][c1] + F[7][c1]));
-            const double n6 = (F[5][c1] + C13 * t) * (1 - wi) + F[6][c1] * wi;
-            const double n13 = (F[12][c1] + C16 * t + tnx) * (1 - wi) + F[13][c1] * wi;
-            const double n14 = (F[11][c1] + C16 * t - tnx) * (1 - wi) + F[14][c1] * wi;
-            const double n17 = (F[16][c1] + C16 * t + tny) * (1 - wi) + F[17][c1] * wi;
-            const double n18 = (F[15][c1] + C16 * t - tny) * (1 - wi) + F[18][c1] * wi;
-            F[6][c1] = n6; F[13][c1] = n13; F[14][c1] = n14; F[17][c1] = n17; F[18][c1] = n18;
+            const double tnx = 0.5 * (F[2][X(c1)] + F[8][X(c1)] + F[10][X(c1)] - (F[1][X(c1)] + F[7][X(c1)] + F[9][X(c1)]));
+            const double tny = 0.5 * (F[4][X(c1)] + F[9][X(c1)] + F[10][X(c1)] - (F[3][X(c1)] + F[8][X(c1)] + F[7][X(c1)]));
+            const double n6 = (F[5][X(c1)] + C13 * t) * (1 - wi) + F[6][X(c1)] * wi;
+            const double n13 = (F[12][X(c1)] + C16 * t + tnx) * (1 - wi) + F[13][X(c1)] * wi;
+            const double n14 = (F[11][X(c1)] + C16 * t - tnx) * (1 - wi) + F[14][X(c1)] * wi;
+            const double n17 = (F[16][X(c1)] + C16 * t + tny) * (1 - wi) + F[17][X(c1)] * wi;
+            const double n18 = (F[15][X(c1)] + C16 * t - tny) * (1 - wi) + F[18][X(c1)] * wi;
+            F[6][X(c1)] = n6; F[13][X(c1)] = n13; F[14][X(c1)] = n14; F[17][X(c1)] = n17; F[18][X(c1)] = n18;
         }
     }
 }
@@ -115,6 +123,7 @@ __global__ void k_outlet_convective(const Dev P) {
         P.phi[cp + 2 * sxy] = v;
         P.phi[cp + 3 * sxy] = v;
     }
+    if (P.sparse && wi) return;
 #pragma unroll
     for (int fl = 0; fl < (MP ? 2 : 1); fl++) {
         double *const *F = fl == 0 ? P.f : P.gg;
@@ -122,18 +131,18 @@ __global__ void k_outlet_convective(const Dev P) {
 #define CB(q) cb[(q)*sxy + c2]
         if (!AFTER) {
             double v;
-            v = ((CB(6) + uc * F[6][cn]) * temp) * (1 - wi) + F[6][cp] * wi;                 F[6][cp] = v;       CB(6) = v;
-            v = ((CB(13) + uc * F[13][cn - 1]) * temp) * (1 - wi) + F[13][cp - 1] * wi;      F[13][cp - 1] = v;  CB(13) = v;
-            v = ((CB(14) + uc * F[14][cn + 1]) * temp) * (1 - wi) + F[14][cp + 1] * wi;      F[14][cp + 1] = v;  CB(14) = v;
-            v = ((CB(17) + uc * F[17][cn - sx]) * temp) * (1 - wi) + F[17][cp - sx] * wi;    F[17][cp - sx] = v; CB(17) = v;
-            v = ((CB(18) + uc * F[18][cn + sx]) * temp) * (1 - wi) + F[18][cp + sx] * wi;    F[18][cp + sx] = v; CB(18) = v;
+            v = ((CB(6) + uc * F[6][X(cn)]) * temp) * (1 - wi) + F[6][X(cp)] * wi;                 F[6][X(cp)] = v;       CB(6) = v;
+            v = ((CB(13) + uc * F[13][X(cn - 1)]) * temp) * (1 - wi) + F[13][X(cp - 1)] * wi;      F[13][X(cp - 1)] = v;  CB(13) = v;
+            v = ((CB(14) + uc * F[14][X(cn + 1)]) * temp) * (1 - wi) + F[14][X(cp + 1)] * wi;      F[14][X(cp + 1)] = v;  CB(14) = v;
+            v = ((CB(17) + uc * F[17][X(cn - sx)]) * temp) * (1 - wi) + F[17][X(cp - sx)] * wi;    F[17][X(cp - sx)] = v; CB(17) = v;
+            v = ((CB(18) + uc * F[18][X(cn + sx)]) * temp) * (1 - wi) + F[18][X(cp + sx)] * wi;    F[18][X(cp + sx)] = v; CB(18) = v;
         } else {
             double v;
-            v = ((CB(6) + uc * F[5][cm]) * temp) * (1 - wi) + F[5][cn] * wi;     F[5][cn] = v;  CB(6) = v;
-            v = ((CB(14) + uc * F[11][cm]) * temp) * (1 - wi) + F[11][cn] * wi;  F[11][cn] = v; CB(14) = v;
-            v = ((CB(13) + uc * F[12][cm]) * temp) * (1 - wi) + F[12][cn] * wi;  F[12][cn] = v; CB(13) = v;
-            v = ((CB(18) + uc * F[15][cm]) * temp) * (1 - wi) + F[15][cn] * wi;  F[15][cn] = v; CB(18) = v;
-            v = ((CB(17) + uc * F[16][cm]) * temp) * (1 - wi) + F[16][cn] * wi;  F[16][cn] = v; CB(17) = v;
+            v = ((CB(6) + uc * F[5][X(cm)]) * temp) * (1 - wi) + F[5][X(cn)] * wi;     F[5][X(cn)] = v;  CB(6) = v;
+            v = ((CB(14) + uc * F[11][X(cm)]) * temp) * (1 - wi) + F[11][X(cn)] * wi;  F[11][X(cn)] = v; CB(14) = v;
+            v = ((CB(13) + uc * F[12][X(cm)]) * temp) * (1 - wi) + F[12][X(cn)] * wi;  F[12][X(cn)] = v; CB(13) = v;
+            v = ((CB(18) + uc * F[15][X(cm)]) * temp) * (1 - wi) + F[15][X(cn)] * wi;  F[15][X(cn)] = v; CB(18) = v;
+            v = ((CB(17) + uc * F[16][X(cm)]) * temp) * (1 - wi) + F[16][X(cn)] * wi;  F[16][X(cn)] = v; CB(17) = v;
         }
 #undef CB
     }
@@ -152,32 +161,33 @@ __global__ void k_outlet_pressure(const Dev P) {
         phin = P.phi[cn];
         P.phi[cp] = phin; P.phi[cp + sxy] = phin; P.phi[cp + 2 * sxy] = phin; P.phi[cp + 3 * sxy] = phin;
     }
+    if (P.sparse && wi) return;
     double *const *F = P.f;
     double *const *G = P.gg;
     double tmp1, tmp2 = 0.0;
     if (!AFTER) {
         if (MP)
-            tmp1 = (F[0][cn] + F[1][cn - 1] + F[2][cn + 1] + F[3][cn - sx] + F[4][cn + sx] + F[7][cn - 1 - sx] + F[8][cn + 1 - sx] +
-                    F[9][cn - 1 + sx] + F[10][cn + 1 + sx] +
-                    2.0 * (F[5][cm] + F[11][cm - 1] + F[12][cm + 1] + F[15][cm - sx] + F[16][cm + sx]) + G[0][cn] + G[1][cn - 1] +
-                    G[2][cn + 1] + G[3][cn - sx] + G[4][cn + sx] + G[7][cn - 1 - sx] + G[8][cn + 1 - sx] + G[9][cn - 1 + sx] +
-                    G[10][cn + 1 + sx] + 2.0 * (G[5][cm] + G[11][cm - 1] + G[12][cm + 1] + G[15][cm - sx] + G[16][cm + sx])) -
+            tmp1 = (F[0][X(cn)] + F[1][X(cn - 1)] + F[2][X(cn + 1)] + F[3][X(cn - sx)] + F[4][X(cn + sx)] + F[7][X(cn - 1 - sx)] + F[8][X(cn + 1 - sx)] +
+                    F[9][X(cn - 1 + sx)] + F[10][X(cn + 1 + sx)] +
+                    2.0 * (F[5][X(cm)] + F[11][X(cm - 1)] + F[12][X(cm + 1)] + F[15][X(cm - sx)] + F[16][X(cm + sx)]) + G[0][X(cn)] + G[1][X(cn - 1)] +
+                    G[2][X(cn + 1)] + G[3][X(cn - sx)] + G[4][X(cn + sx)] + G[7][X(cn - 1 - sx)] + G[8][X(cn + 1 - sx)] + G[9][X(cn - 1 + sx)] +
+                    G[10][X(cn + 1 + sx)] + 2.0 * (G[5][X(cm)] + G[11][X(cm - 1)] + G[12][X(cm + 1)] + G[15][X(cm - sx)] + G[16][X(cm + sx)])) -
                    P.rho_out;
         else
-            tmp1 = (F[0][cn] + F[1][cn - 1] + F[2][cn + 1] + F[3][cn - sx] + F[4][cn + sx] + F[7][cn - 1 - sx] + F[8][cn + 1 - sx] +
-                    F[9][cn - 1 + sx] + F[10][cn + 1 + sx] +
-                    2.0 * (F[5][cm] + F[11][cm - 1] + F[12][cm + 1] + F[15][cm - sx] + F[16][cm + sx])) -
+            tmp1 = (F[0][X(cn)] + F[1][X(cn - 1)] + F[2][X(cn + 1)] + F[3][X(cn - sx)] + F[4][X(cn + sx)] + F[7][X(cn - 1 - sx)] + F[8][X(cn + 1 - sx)] +
+                    F[9][X(cn - 1 + sx)] + F[10][X(cn + 1 + sx)] +
+                    2.0 * (F[5][X(cm)] + F[11][X(cm - 1)] + F[12][X(cm + 1)] + F[15][X(cm - sx)] + F[16][X(cm + sx)])) -
                    P.rho_out;
     } else {
         if (MP)
-            tmp1 = (F[0][cn] + F[2][cn] + F[1][cn] + F[4][cn] + F[3][cn] + F[8][cn] + F[7][cn] + F[10][cn] + F[9][cn] +
-                    2.0 * (F[6][cn] + F[14][cn] + F[13][cn] + F[18][cn] + F[17][cn]) + G[0][cn] + G[2][cn] + G[1][cn] + G[4][cn] +
-                    G[3][cn] + G[8][cn] + G[7][cn] + G[10][cn] + G[9][cn] +
-                    2.0 * (G[6][cn] + G[14][cn] + G[13][cn] + G[18][cn] + G[17][cn])) -
+            tmp1 = (F[0][X(cn)] + F[2][X(cn)] + F[1][X(cn)] + F[4][X(cn)] + F[3][X(cn)] + F[8][X(cn)] + F[7][X(cn)] + F[10][X(cn)] + F[9][X(cn)] +
+                    2.0 * (F[6][X(cn)] + F[14][X(cn)] + F[13][X(cn)] + F[18][X(cn)] + F[17][X(cn)]) + G[0][X(cn)] + G[2][X(cn)] + G[1][X(cn)] + G[4][X(cn)] +
+                    G[3][X(cn)] + G[8][X(cn)] + G[7][X(cn)] + G[10][X(cn)] + G[9][X(cn)] +
+                    2.0 * (G[6][X(cn)] + G[14][X(cn)] + G[13][X(cn)] + G[18][X(cn)] + G[17][X(cn)])) -
                    P.rho_out;
         else
-            tmp1 = (F[0][cn] + F[2][cn] + F[1][cn] + F[4][cn] + F[3][cn] + F[8][cn] + F[7][cn] + F[10][cn] + F[9][cn] +
-                    2.0 * (F[6][cn] + F[14][cn] + F[13][cn] + F[18][cn] + F[17][cn])) -
+            tmp1 = (F[0][X(cn)] + F[2][X(cn)] + F[1][X(cn)] + F[4][X(cn)] + F[3][X(cn)] + F[8][X(cn)] + F[7][X(cn)] + F[10][X(cn)] + F[9][X(cn)] +
+                    2.0 * (F[6][X(cn)] + F[14][X(cn)] + F[13][X(cn)] + F[18][X(cn)] + F[17][X(cn)])) -
                    P.rho_out;
     }
     if (MP) {
@@ -189,22 +199,22 @@ __global__ void k_outlet_pressure(const Dev P) {
         double *const *H = fl == 0 ? P.f : P.gg;
         const double t = fl == 0 ? tmp1 : tmp2;
         if (!AFTER) {
-            const double tnx = 0.5 * (H[1][cn - 1] + H[7][cn - 1 - sx] + H[9][cn - 1 + sx] - (H[2][cn + 1] + H[8][cn + 1 - sx] + H[10][cn + 1 + sx]));
-            const double tny = 0.5 * (H[3][cn - sx] + H[7][cn - 1 - sx] + H[8][cn + 1 - sx] - (H[4][cn + sx] + H[10][cn + 1 + sx] + H[9][cn - 1 + sx]));
-            H[6][cp] = (H[5][cm] - C13 * t) * dwi + H[6][cp] * wi;
-            H[13][cp - 1] = (H[12][cm + 1] - C16 * t - tnx) * dwi + H[13][cp - 1] * wi;
-            H[14][cp + 1] = (H[11][cm - 1] - C16 * t + tnx) * dwi + H[14][cp + 1] * wi;
-            H[17][cp - sx] = (H[16][cm + sx] - C16 * t - tny) * dwi + H[17][cp - sx] * wi;
-            H[18][cp + sx] = (H[15][cm - sx] - C16 * t + tny) * dwi + H[18][cp + sx] * wi;
+            const double tnx = 0.5 * (H[1][X(cn - 1)] + H[7][X(cn - 1 - sx)] + H[9][X(cn - 1 + sx)] - (H[2][X(cn + 1)] + H[8][X(cn + 1 - sx)] + H[10][X(cn + 1 + sx)]));
+            const double tny = 0.5 * (H[3][X(cn - sx)] + H[7][X(cn - 1 - sx)] + H[8][X(cn + 1 - sx)] - (H[4][X(cn + sx)] + H[10][X(cn + 1 + sx)] + H[9][X(cn - 1 + sx)]));
+            H[6][X(cp)] = (H[5][X(cm)] - C13 * t) * dwi + H[6][X(cp)] * wi;
+            H[13][X(cp - 1)] = (H[12][X(cm + 1)] - C16 * t - tnx) * dwi + H[13][X(cp - 1)] * wi;
+            H[14][X(cp + 1)] = (H[11][X(cm - 1)] - C16 * t + tnx) * dwi + H[14][X(cp + 1)] * wi;
+            H[17][X(cp - sx)] = (H[16][X(cm + sx)] - C16 * t - tny) * dwi + H[17][X(cp - sx)] * wi;
+            H[18][X(cp + sx)] = (H[15][X(cm - sx)] - C16 * t + tny) * dwi + H[18][X(cp + sx)] * wi;
         } else {
-            const double tnx = 0.5 * (H[2][cn] + H[8][cn] + H[10][cn] - (H[1][cn] + H[7][cn] + H[9][cn]));
-            const double tny = 0.5 * (H[4][cn] + H[10][cn] + H[9][cn] - (H[3][cn] + H[7][cn] + H[8][cn]));
-            const double n5 = (H[6][cn] - C13 * t) * dwi + H[5][cn] * wi;
-            const double n11 = (H[14][cn] - C16 * t + tnx) * dwi + H[11][cn] * wi;
-            const double n12 = (H[13][cn] - C16 * t - tnx) * dwi + H[12][cn] * wi;
-            const double n15 = (H[18][cn] - C16 * t + tny) * dwi + H[15][cn] * wi;
-            const double n16 = (H[17][cn] - C16 * t - tny) * dwi + H[16][cn] * wi;
-            H[5][cn] = n5; H[11][cn] = n11; H[12][cn] = n12; H[15][cn] = n15; H[16][cn] = n16;
+            const double tnx = 0.5 * (H[2][X(cn)] + H[8][X(cn)] + H[10][X(cn)] - (H[1][X(cn)] + H[7][X(cn)] + H[9][X(cn)]));
+            const double tny = 0.5 * (H[4][X(cn)] + H[10][X(cn)] + H[9][X(cn)] - (H[3][X(cn)] + H[7][X(cn)] + H[8][X(cn)]));
+            const double n5 = (H[6][X(cn)] - C13 * t) * dwi + H[5][X(cn)] * wi;
+            const double n11 = (H[14][X(cn)] - C16 * t + tnx) * dwi + H[11][X(cn)] * wi;
+            const double n12 = (H[13][X(cn)] - C16 * t - tnx) * dwi + H[12][X(cn)] * wi;
+            const double n15 = (H[18][X(cn)] - C16 * t + tny) * dwi + H[15][X(cn)] * wi;
+            const double n16 = (H[17][X(cn)] - C16 * t - tny) * dwi + H[16][X(cn)] * wi;
+            H[5][X(cn)] = n5; H[11][X(cn)] = n11; H[12][X(cn)] = n12; H[15][X(cn)] = n15; H[16][X(cn)] = n16;
         }
     }
 }
@@ -219,31 +229,31 @@ __global__ void k_porous_plate(const Dev P, int zp, int block_fluid1) {
     double *const *B = block_fluid1 ? P.f : P.gg;
     double *const *T = block_fluid1 ? P.gg : P.f;
     if (!AFTER) {
-        B[6][c] = B[5][cm];
-        B[13][c - 1] = B[12][cm];
-        B[14][c + 1] = B[11][cm];
-        B[17][c - sx] = B[16][cm];
-        B[18][c + sx] = B[15][cm];
-        B[5][c] = B[6][cp];
-        B[12][c + 1] = B[13][cp];
-        B[11][c - 1] = B[14][cp];
-        B[16][c + sx] = B[17][cp];
-        B[15][c - sx] = B[18][cp];
-        T[6][c] = T[6][cp]; T[13][c] = T[13][cp]; T[14][c] = T[14][cp]; T[17][c] = T[17][cp]; T[18][c] = T[18][cp];
-        T[5][c] = T[5][cm]; T[12][c] = T[12][cm]; T[11][c] = T[11][cm]; T[16][c] = T[16][cm]; T[15][c] = T[15][cm];
+        B[6][X(c)] = B[5][X(cm)];
+        B[13][X(c - 1)] = B[12][X(cm)];
+        B[14][X(c + 1)] = B[11][X(cm)];
+        B[17][X(c - sx)] = B[16][X(cm)];
+        B[18][X(c + sx)] = B[15][X(cm)];
+        B[5][X(c)] = B[6][X(cp)];
+        B[12][X(c + 1)] = B[13][X(cp)];
+        B[11][X(c - 1)] = B[14][X(cp)];
+        B[16][X(c + sx)] = B[17][X(cp)];
+        B[15][X(c - sx)] = B[18][X(cp)];
+        T[6][X(c)] = T[6][X(cp)]; T[13][X(c)] = T[13][X(cp)]; T[14][X(c)] = T[14][X(cp)]; T[17][X(c)] = T[17][X(cp)]; T[18][X(c)] = T[18][X(cp)];
+        T[5][X(c)] = T[5][X(cm)]; T[12][X(c)] = T[12][X(cm)]; T[11][X(c)] = T[11][X(cm)]; T[16][X(c)] = T[16][X(cm)]; T[15][X(c)] = T[15][X(cm)];
     } else {
-        B[5][cm] = B[6][c];
-        B[11][cm] = B[14][c + 1];
-        B[12][cm] = B[13][c - 1];
-        B[15][cm] = B[18][c + sx];
-        B[16][cm] = B[17][c - sx];
-        B[6][cp] = B[5][c];
-        B[14][cp] = B[11][c - 1];
-        B[13][cp] = B[12][c + 1];
-        B[18][cp] = B[15][c - sx];
-        B[17][cp] = B[16][c + sx];
-        T[5][cm] = T[5][c]; T[11][cm] = T[11][c]; T[12][cm] = T[12][c]; T[15][cm] = T[15][c]; T[16][cm] = T[16][c];
-        T[6][cp] = T[6][c]; T[14][cp] = T[14][c]; T[13][cp] = T[13][c]; T[18][cp] = T[18][c]; T[17][cp] = T[17][c];
+        B[5][X(cm)] = B[6][X(c)];
+        B[11][X(cm)] = B[14][X(c + 1)];
+        B[12][X(cm)] = B[13][X(c - 1)];
+        B[15][X(cm)] = B[18][X(c + sx)];
+        B[16][X(cm)] = B[17][X(c - sx)];
+        B[6][X(cp)] = B[5][X(c)];
+        B[14][X(cp)] = B[11][X(c - 1)];
+        B[13][X(cp)] = B[12][X(c + 1)];
+        B[18][X(cp)] = B[15][X(c - sx)];
+        B[17][X(cp)] = B[16][X(c + sx)];
+        T[5][X(cm)] = T[5][X(c)]; T[11][X(cm)] = T[11][X(c)]; T[12][X(cm)] = T[12][X(c)]; T[15][X(cm)] = T[15][X(c)]; T[16][X(cm)] = T[16][X(c)];
+        T[6][X(cp)] = T[6][X(c)]; T[14][X(cp)] = T[14][X(c)]; T[13][X(cp)] = T[13][X(c)]; T[18][X(cp)] = T[18][X(c)]; T[17][X(cp)] = T[17][X(c)];
     }
 }
 

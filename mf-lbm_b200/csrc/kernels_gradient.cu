@@ -48,12 +48,15 @@ __global__ void __launch_bounds__(128) k_gradient(const Dev P) {
     const int k = (int)blockIdx.z - 1;
     if (i > P.g.nx + 2) return;
     const int c = P.g.cell(i, j, k);
+    // solid nodes: the reference zeroes n and |grad phi| there every call; they are zero-initialised and only K6
+    // ever writes n at solid-boundary nodes (fully, after this kernel), so skipping the store is unobservable.
+    if (P.walls[c] == 1) return;
     const int sx = P.g.sx, sxy = P.g.sxy;
     const double *__restrict__ ph = P.phi;
     auto v = [&](int a, int b, int d) { return ph[c + a + sx * b + sxy * d]; };
     const double gx = ddx(v), gy = ddy(v), gz = ddz(v);
     const double cn = sqrt(gx * gx + gy * gy + gz * gz);
-    if (cn < 1e-6 || P.walls[c] == 1) {
+    if (cn < 1e-6) {
         P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
     } else {
         P.cn_x[c] = gx / cn; P.cn_y[c] = gy / cn; P.cn_z[c] = gz / cn; P.c_norm[c] = cn;
@@ -117,6 +120,9 @@ __global__ void __launch_bounds__(128) k_curvature(const Dev P) {
     const int k = blockIdx.z + 1;
     if (i > P.g.nx) return;
     const int c = P.g.cell(i, j, k);
+    // the reference evaluates the curvature at solid nodes too (MP/Phase_gradient.F90:121, test commented out);
+    // nothing on the hot path consumes it there, so it is only produced when full_curv is set.
+    if (!P.full_curv && P.walls[c] != 0) return;
     const int sx = P.g.sx, sxy = P.g.sxy;
     const double *__restrict__ px = P.cn_x;
     const double *__restrict__ py = P.cn_y;

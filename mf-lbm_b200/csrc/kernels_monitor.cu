@@ -9,15 +9,24 @@
 
 namespace mflbm {
 
-template <bool MP>
+template <bool MP, bool SPARSE>
 __global__ void __launch_bounds__(128) k_macro(const Dev P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
-    if (i > P.g.nx) return;
-    const int c = P.g.cell(i, j, k);
-    const int wi = P.walls[c];
+    int c, cl;
+    if (SPARSE) {  // fluid nodes only; u,v,w,rho are zero at solid nodes (they are zero-initialised and never written)
+        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= P.nA) return;
+        c = P.cellA[n];
+        cl = n;
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+        if (i > P.g.nx) return;
+        c = P.g.cell(i, j, k);
+        cl = c;
+    }
+    const int wi = SPARSE ? 0 : P.walls[c];
     double ft[19];
 #pragma unroll
-    for (int q = 0; q < 19; q++) ft[q] = MP ? P.f[q][c] + P.gg[q][c] : P.f[q][c];
+    for (int q = 0; q < 19; q++) ft[q] = MP ? P.f[q][cl] + P.gg[q][cl] : P.f[q][cl];
     P.rho[c] = (ft[0] + ft[1] + ft[2] + ft[3] + ft[4] + ft[5] + ft[6] + ft[7] + ft[8] + ft[9] + ft[10] + ft[11] + ft[12] + ft[13] +
                 ft[14] + ft[15] + ft[16] + ft[17] + ft[18]) * (1 - wi);
     double fx = 0.0, fy = 0.0, fz = P.force_Z;
@@ -30,14 +39,36 @@ __global__ void __launch_bounds__(128) k_macro(const Dev P) {
     P.u[c] = (ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - 0.5 * fx) * (1 - wi);
     P.v[c] = (ft[3] - ft[4] + ft[7] + ft[8] - ft[9] - ft[10] + ft[15] - ft[16] + ft[17] - ft[18] - 0.5 * fy) * (1 - wi);
     P.w[c] = (ft[5] - ft[6] + ft[11] + ft[12] - ft[13] - ft[14] + ft[15] + ft[16] - ft[17] - ft[18] - 0.5 * fz) * (1 - wi);
-    if (MP) P.phi[c] = 0.0 * wi + P.phi[c] * (1 - wi);
+    if (MP && !SPARSE) P.phi[c] = 0.0 * wi + P.phi[c] * (1 - wi);
+}
+
+// phi <- 0 at solid nodes of 1..n (last statement of compute_macro_vars, MP/Misc.F90:424) for the sparse layout
+__global__ void __launch_bounds__(128) k_phi_zero_walls(const Dev P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > P.g.nx) return;
+    const int c = P.g.cell(i, j, k);
+    const int wi = P.walls[c];
+    if (wi) P.phi[c] = 0.0 * wi + P.phi[c] * (1 - wi);
 }
 
 void launch_macro(mflbm_ctx *c, cudaStream_t st) {
     const Dev &P = c->d;
     dim3 grid((P.g.nx + 127) / 128, P.g.ny, P.g.nz);
-    if (P.multiphase) k_macro<true><<<grid, 128, 0, st>>>(P);
-    else k_macro<false><<<grid, 128, 0, st>>>(P);
+    if (P.sparse) {
+        const int nb = (P.nA + 127) / 128;
+        if (nb > 0) {
+            if (P.multiphase) k_macro<true, true><<<nb, 128, 0, st>>>(P);
+            else k_macro<false, true><<<nb, 128, 0, st>>>(P);
+            c->launches++;
+        }
+        if (P.multiphase) {
+            k_phi_zero_walls<<<grid, 128, 0, st>>>(P);
+            c->launches++;
+        }
+        return;
+    }
+    if (P.multiphase) k_macro<true, false><<<grid, 128, 0, st>>>(P);
+    else k_macro<false, false><<<grid, 128, 0, st>>>(P);
     c->launches++;
 }
 

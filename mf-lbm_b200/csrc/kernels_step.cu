@@ -1,36 +1,57 @@
-// kernels_step.cu -- collision + AA-pattern in-place streaming (reference-order dataflow).
+// kernels_step.cu -- collision + AA-pattern in-place streaming.
 //
 // Replaces kernel_odd_color / kernel_even_color (MP/Kernel_multiphase.F90:6-362, :371-725) and
-// kernel_odd / kernel_even (SP/Kernel.F90:5-200, :206-400).  One thread per lattice node, x fastest
-// (rows are 128-byte aligned so the even step is perfectly coalesced; the odd step touches the +-1
-// neighbours in x/y/z).  Solid nodes are skipped but their slots stay live storage for bounced
-// populations exactly as in the reference.
+// kernel_odd / kernel_even (SP/Kernel.F90:5-200, :206-400).  One thread per fluid node.
+//
+// Two population layouts share this kernel (template parameter SPARSE):
+//  * dense  : the reference's direct addressing on the padded grid; solid nodes are skipped but their slots
+//             are live storage for bounced populations.
+//  * sparse : populations exist only for ACTIVE nodes (fluid nodes in raster order, then the solid-boundary /
+//             ghost nodes they stream into).  Warps are fully populated with fluid nodes, which is what the
+//             FP64 pipe and the HBM sectors want in porous media (MLUPS counts fluid nodes only,
+//             MP/Main_multiphase.F90:540).  The even step is node-local and needs no addressing at all; the odd
+//             step reads the 18 neighbour indices of the node (coalesced int32 rows).  Same 38 addresses are
+//             read and written per node, so the update stays race-free in any order, like the reference.
 #include "collide.cuh"
 
 namespace mflbm {
 
-template <bool MP, bool ODD>
-__global__ void __launch_bounds__(128) k_collide(const Dev P, int k0) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    const int j = blockIdx.y + 1;
-    const int k = blockIdx.z + k0;
-    if (i > P.g.nx) return;
-    const int c = P.g.cell(i, j, k);
-    if (P.walls[c] != 0) return;
+template <bool MP, bool ODD, bool SPARSE>
+__global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, int n1) {
+    int c, n = 0;
+    if (SPARSE) {
+        n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= n1) return;
+        c = P.cellA[n];
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+        const int j = blockIdx.y + 1;
+        const int k = blockIdx.z + k0;
+        if (i > P.g.nx) return;
+        c = P.g.cell(i, j, k);
+        if (P.walls[c] != 0) return;
+    }
 
     double a[19], b[19];
-    if (ODD) {  // pull f_q from x - e_q (MP/Kernel_multiphase.F90:46-84)
+    int nb[19];  // sparse odd step: active index of x+e_q
+    if (ODD) {   // pull f_q from x - e_q (MP/Kernel_multiphase.F90:46-84)
+        if (SPARSE) {
+            nb[0] = n;
+#pragma unroll
+            for (int q = 1; q < 19; q++) nb[q] = __ldg(P.nbr + (q - 1) * P.nbr_stride + n);
+        }
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            const int cq = c - P.g.off(q);
+            const int cq = SPARSE ? nb[OPC(q)] : c - P.g.off(q);
             a[q] = P.f[q][cq];
             if (MP) b[q] = P.gg[q][cq];
         }
     } else {  // node-local, direction-swapped slots (MP/Kernel_multiphase.F90:410-448)
+        const int cl = SPARSE ? n : c;
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            a[q] = P.f[OPC(q)][c];
-            if (MP) b[q] = P.gg[OPC(q)][c];
+            a[q] = P.f[OPC(q)][cl];
+            if (MP) b[q] = P.gg[OPC(q)][cl];
         }
     }
 
@@ -42,41 +63,59 @@ __global__ void __launch_bounds__(128) k_collide(const Dev P, int k0) {
     }
 
     if (ODD) {  // push q into slot opc(q) of x + e_q (MP/Kernel_multiphase.F90:318-354)
-        P.f[0][c] = a[0];
-        if (MP) P.gg[0][c] = b[0];
+        const int cl = SPARSE ? n : c;
+        P.f[0][cl] = a[0];
+        if (MP) P.gg[0][cl] = b[0];
 #pragma unroll
         for (int q = 1; q < 19; q++) {
-            const int cq = c + P.g.off(q);
+            const int cq = SPARSE ? nb[q] : c + P.g.off(q);
             P.f[OPC(q)][cq] = a[q];
             if (MP) P.gg[OPC(q)][cq] = b[q];
         }
     } else {
+        const int cl = SPARSE ? n : c;
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            P.f[q][c] = a[q];
-            if (MP) P.gg[q][c] = b[q];
+            P.f[q][cl] = a[q];
+            if (MP) P.gg[q][cl] = b[q];
         }
     }
 }
 
-void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1) {
-    if (k1 < k0) return;
+template <bool SPARSE>
+static void launch_collide_t(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1) {
     const Dev &P = c->d;
-    dim3 block(128);
-    dim3 grid((P.g.nx + 127) / 128, P.g.ny, k1 - k0 + 1);
-    if (P.multiphase) {
-        if (odd) k_collide<true, true><<<grid, block, 0, st>>>(P, k0);
-        else k_collide<true, false><<<grid, block, 0, st>>>(P, k0);
+    dim3 block(128), grid;
+    int n0 = 0, n1 = 0;
+    if (SPARSE) {
+        n0 = c->kstartA[k0];
+        n1 = c->kstartA[k1 + 1];
+        if (n1 <= n0) return;
+        grid = dim3((n1 - n0 + 127) / 128);
     } else {
-        if (odd) k_collide<false, true><<<grid, block, 0, st>>>(P, k0);
-        else k_collide<false, false><<<grid, block, 0, st>>>(P, k0);
+        grid = dim3((P.g.nx + 127) / 128, P.g.ny, k1 - k0 + 1);
+    }
+    if (P.multiphase) {
+        if (odd) k_collide<true, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        else k_collide<true, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+    } else {
+        if (odd) k_collide<false, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        else k_collide<false, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     }
     c->launches++;
+}
+
+void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1) {
+    if (k1 < k0) return;
+    if (c->d.sparse) launch_collide_t<true>(c, st, odd, k0, k1);
+    else launch_collide_t<false>(c, st, odd, k0, k1);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // periodic z on one GPU: the reference's self send/recv through the periodic Cartesian communicator
 // (MP/Mpi.F90:101-346 pull, :354-598 push, :608-867 phi).  One launch moves all planes.
+// Sparse layout: a copy is skipped when either end is not an active node -- such a slot has no fluid
+// consumer (the only consumer of slot q at y is y+e_q), so the skipped copy is unobservable.
 // ---------------------------------------------------------------------------------------------------
 template <bool MP>
 __global__ void k_wrap_z(const Dev P, int push) {
@@ -84,27 +123,7 @@ __global__ void k_wrap_z(const Dev P, int push) {
     const int j = blockIdx.y + 1;
     if (i > P.g.nx) return;
     const int nz = P.g.nz;
-    const int c0 = P.g.cell(i, j, 0), c1 = P.g.cell(i, j, 1), cn = P.g.cell(i, j, nz), cn1 = P.g.cell(i, j, nz + 1);
-    constexpr int qM[5] = {6, 14, 13, 18, 17};  // e_z = -1
-    constexpr int qP[5] = {5, 11, 12, 15, 16};  // e_z = +1
-#pragma unroll
-    for (int m = 0; m < 5; m++) {
-        if (!push) {
-            P.f[qM[m]][cn1] = P.f[qM[m]][c1];
-            P.f[qP[m]][c0] = P.f[qP[m]][cn];
-            if (MP) {
-                P.gg[qM[m]][cn1] = P.gg[qM[m]][c1];
-                P.gg[qP[m]][c0] = P.gg[qP[m]][cn];
-            }
-        } else {
-            P.f[qP[m]][cn] = P.f[qP[m]][c0];
-            P.f[qM[m]][c1] = P.f[qM[m]][cn1];
-            if (MP) {
-                P.gg[qP[m]][cn] = P.gg[qP[m]][c0];
-                P.gg[qM[m]][c1] = P.gg[qM[m]][cn1];
-            }
-        }
-    }
+    int c0 = P.g.cell(i, j, 0), c1 = P.g.cell(i, j, 1), cn = P.g.cell(i, j, nz), cn1 = P.g.cell(i, j, nz + 1);
     if (MP) {
 #pragma unroll
         for (int kk = 1; kk <= 4; kk++) {
@@ -112,6 +131,36 @@ __global__ void k_wrap_z(const Dev P, int push) {
             const double hi = P.phi[P.g.cell(i, j, nz + kk - 4)];
             P.phi[P.g.cell(i, j, kk - 4)] = hi;
             P.phi[P.g.cell(i, j, kk + nz)] = lo;
+        }
+    }
+    bool lo_ok = true, hi_ok = true;  // pull: (1 -> nz+1) and (nz -> 0); push: (nz+1 -> 1) and (0 -> nz)
+    if (P.sparse) {
+        c0 = P.smap[c0]; c1 = P.smap[c1]; cn = P.smap[cn]; cn1 = P.smap[cn1];
+        lo_ok = c1 >= 0 && cn1 >= 0;
+        hi_ok = c0 >= 0 && cn >= 0;
+    }
+    constexpr int qM[5] = {6, 14, 13, 18, 17};  // e_z = -1
+    constexpr int qP[5] = {5, 11, 12, 15, 16};  // e_z = +1
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+        if (!push) {
+            if (lo_ok) {
+                P.f[qM[m]][cn1] = P.f[qM[m]][c1];
+                if (MP) P.gg[qM[m]][cn1] = P.gg[qM[m]][c1];
+            }
+            if (hi_ok) {
+                P.f[qP[m]][c0] = P.f[qP[m]][cn];
+                if (MP) P.gg[qP[m]][c0] = P.gg[qP[m]][cn];
+            }
+        } else {
+            if (hi_ok) {
+                P.f[qP[m]][cn] = P.f[qP[m]][c0];
+                if (MP) P.gg[qP[m]][cn] = P.gg[qP[m]][c0];
+            }
+            if (lo_ok) {
+                P.f[qM[m]][c1] = P.f[qM[m]][cn1];
+                if (MP) P.gg[qM[m]][c1] = P.gg[qM[m]][cn1];
+            }
         }
     }
 }
@@ -122,6 +171,102 @@ void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push) {
     dim3 grid((P.g.nx + 127) / 128, P.g.ny);
     if (P.multiphase) k_wrap_z<true><<<grid, block, 0, st>>>(P, push ? 1 : 0);
     else k_wrap_z<false><<<grid, block, 0, st>>>(P, push ? 1 : 0);
+    c->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sparse layout helpers
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_fill_smap(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.nAct) P.smap[P.cellA[n]] = n;
+}
+
+void launch_fill_smap(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    cudaMemsetAsync(P.smap, 0xff, (size_t)P.g.ntot * sizeof(int), st);
+    k_fill_smap<<<(P.nAct + 255) / 256, 256, 0, st>>>(P);
+    c->launches++;
+}
+
+// caller's (0:nx+1,0:ny+1,0:nz+1) array <-> active-node list
+__global__ void k_repack_sparse(const Dev P, double *pdf, double *packed, int to_dev) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.nAct) return;
+    int c = P.cellA[n] - P.g.base;  // (i-1) + sx*(j+3) + sxy*(k+3)
+    const int k = c / P.g.sxy - 3;
+    c -= (k + 3) * P.g.sxy;
+    int j = c / P.g.sx - 3;
+    int i = c - (j + 3) * P.g.sx + 1;
+    if (i > P.g.nx + 4) {  // low-x ghosts live in the tail padding of the previous row
+        i -= P.g.sx;
+        j += 1;
+    }
+    const size_t p = (size_t)i + (size_t)(P.g.nx + 2) * ((size_t)j + (size_t)(P.g.ny + 2) * k);
+    if (to_dev) pdf[n] = packed[p];
+    else packed[p] = pdf[n];
+}
+
+void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev) {
+    const Dev &P = c->d;
+    k_repack_sparse<<<(P.nAct + 255) / 256, 256, 0, st>>>(P, pdf, packed, to_dev ? 1 : 0);
+    c->launches++;
+}
+
+// NVLink halo exchange, sparse layout: gather/scatter the 5 (+5) z-crossing populations of the boundary
+// planes into dense nx*ny send/recv buffers (same plane pairs as MP/Mpi.F90:121-143,244-266,374-396,497-519).
+// A non-active source is encoded as a tagged NaN and ignored by the receiver.
+#define MFLBM_HOLE 0x7FF8DEADBEEF0001LL
+template <bool MP>
+__global__ void k_halo_pack(const Dev P, double *buf_lo, double *buf_hi, int push, int unpack) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1;
+    if (i > P.g.nx) return;
+    const int nz = P.g.nz, nxy = P.g.nx * P.g.ny;
+    const int p = (i - 1) + P.g.nx * (j - 1);
+    constexpr int qM[5] = {6, 14, 13, 18, 17};
+    constexpr int qP[5] = {5, 11, 12, 15, 16};
+    // plane used on the low / high side and which population set lives there
+    //   pack  pull: lo = qM @ k=1     hi = qP @ k=nz        unpack pull: lo = qP @ k=0    hi = qM @ k=nz+1
+    //   pack  push: lo = qP @ k=0     hi = qM @ k=nz+1      unpack push: lo = qM @ k=1    hi = qP @ k=nz
+    const bool lo_is_M = (!push && !unpack) || (push && unpack);
+    const int klo = lo_is_M ? 1 : 0;
+    const int khi = lo_is_M ? nz : nz + 1;
+    int clo = P.g.cell(i, j, klo), chi = P.g.cell(i, j, khi);
+    if (P.sparse) {
+        clo = P.smap[clo];
+        chi = P.smap[chi];
+    }
+#pragma unroll
+    for (int fl = 0; fl < (MP ? 2 : 1); fl++) {
+        double *const *F = fl == 0 ? P.f : P.gg;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            const int qlo = lo_is_M ? qM[m] : qP[m];
+            const int qhi = lo_is_M ? qP[m] : qM[m];
+            const int slot = (fl * 5 + m) * nxy + p;
+            if (!unpack) {
+                if (buf_lo) buf_lo[slot] = clo >= 0 ? F[qlo][clo] : __longlong_as_double(MFLBM_HOLE);
+                if (buf_hi) buf_hi[slot] = chi >= 0 ? F[qhi][chi] : __longlong_as_double(MFLBM_HOLE);
+            } else {
+                if (buf_lo && clo >= 0) {
+                    const double v = buf_lo[slot];
+                    if (__double_as_longlong(v) != MFLBM_HOLE) F[qlo][clo] = v;
+                }
+                if (buf_hi && chi >= 0) {
+                    const double v = buf_hi[slot];
+                    if (__double_as_longlong(v) != MFLBM_HOLE) F[qhi][chi] = v;
+                }
+            }
+        }
+    }
+}
+
+void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack) {
+    const Dev &P = c->d;
+    dim3 block(128), grid((P.g.nx + 127) / 128, P.g.ny);
+    if (P.multiphase) k_halo_pack<true><<<grid, block, 0, st>>>(P, buf_lo, buf_hi, push, unpack);
+    else k_halo_pack<false><<<grid, block, 0, st>>>(P, buf_lo, buf_hi, push, unpack);
     c->launches++;
 }
 

@@ -144,6 +144,8 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->nccl = nullptr;
     ctx->comm = nullptr;
     ctx->macro_alloc = false;
+    ctx->pdf_alloc = false;
+    ctx->halo_buf[0] = ctx->halo_buf[1] = ctx->halo_buf[2] = ctx->halo_buf[3] = nullptr;
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
     ctx->red_dev = nullptr;
@@ -188,10 +190,8 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         d.relaxation = cfg->relaxation; d.uin_avg = cfg->uin_avg; d.rho_in = cfg->rho_in; d.rho_out = cfg->rho_out;
         d.s_e = cfg->s_e; d.s_e2 = cfg->s_e2; d.s_q = cfg->s_q; d.s_nu = cfg->s_nu; d.s_pi = cfg->s_pi; d.s_t = cfg->s_t;
         d.rk_weight2 = 1.0 / sqrt(2.0) / 36.0;
-        for (int q = 0; q < 19; q++) {
-            if (dev_alloc(ctx, &d.f[q], ntot)) return MFLBM_ERR_CUDA;
-            if (d.multiphase && dev_alloc(ctx, &d.gg[q], ntot)) return MFLBM_ERR_CUDA;
-        }
+        // the 38 (19) population arrays are allocated at the first upload, once the wall array (and with it the
+        // layout: dense grid or active-node list) is known
         if (dev_alloc(ctx, &d.walls, ntot)) return MFLBM_ERR_CUDA;
         if (dev_alloc(ctx, &d.w_in, (size_t)sxy + 32)) return MFLBM_ERR_CUDA;
         if (dev_alloc(ctx, &d.f_convec, (size_t)19 * sxy + 32)) return MFLBM_ERR_CUDA;
@@ -247,6 +247,8 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->stage) cudaFree(ctx->stage);
+    for (int b = 0; b < 4; b++)
+        if (ctx->halo_buf[b]) cudaFree(ctx->halo_buf[b]);
     if (ctx->red_dev) cudaFree(ctx->red_dev);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
@@ -257,9 +259,136 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
     delete ctx;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Population layout.  Built once from the wall array (host side, integer work only):
+//   A nodes  = fluid nodes (walls==0) of 1..nx,1..ny,1..nz in raster order (k outer, i inner)
+//   S nodes  = every other node of the 0..n+1 box that is a D3Q19 neighbour of an A node
+//   nbr[q-1][n] = active index of x_n + e_q   (always exists by construction)
+// ---------------------------------------------------------------------------------------------------
+static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i fastest */) {
+    Dev &d = ctx->d;
+    const Grid &g = d.g;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const long long bx = nx + 2, by = ny + 2, bz = nz + 2;  // 0..n+1 box
+    auto W = [&](int i, int j, int k) -> int8_t {
+        return walls[(size_t)(i + 1) + (size_t)(nx + 4) * ((size_t)(j + 1) + (size_t)(ny + 4) * (size_t)(k + 1))];
+    };
+    std::vector<int> idx((size_t)(bx * by * bz), -1);
+    auto B = [&](int i, int j, int k) -> size_t { return (size_t)i + (size_t)bx * ((size_t)j + (size_t)by * (size_t)k); };
+    // pass 1: A nodes per plane
+    std::vector<int> cntA(nz + 2, 0), cntS(nz + 2, 0);
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz; k++) {
+        int c = 0;
+        for (int j = 1; j <= ny; j++)
+            for (int i = 1; i <= nx; i++) c += (W(i, j, k) == 0);
+        cntA[k] = c;
+    }
+    ctx->kstartA.assign(nz + 3, 0);
+    for (int k = 1; k <= nz + 1; k++) ctx->kstartA[k] = ctx->kstartA[k - 1] + cntA[k - 1];
+    ctx->kstartA[nz + 2] = ctx->kstartA[nz + 1];
+    const int nA = ctx->kstartA[nz + 1];
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz; k++) {
+        int n = ctx->kstartA[k];
+        for (int j = 1; j <= ny; j++)
+            for (int i = 1; i <= nx; i++)
+                if (W(i, j, k) == 0) idx[B(i, j, k)] = n++;
+    }
+    auto isA = [&](int i, int j, int k) -> bool { return i >= 1 && i <= nx && j >= 1 && j <= ny && k >= 1 && k <= nz && W(i, j, k) == 0; };
+    // pass 2: S nodes (mark with -2), count per plane
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k <= nz + 1; k++) {
+        int c = 0;
+        for (int j = 0; j <= ny + 1; j++)
+            for (int i = 0; i <= nx + 1; i++) {
+                if (isA(i, j, k)) continue;
+                bool s = false;
+                for (int q = 1; q < 19 && !s; q++) s = isA(i + EX(q), j + EY(q), k + EZ(q));
+                if (s) {
+                    idx[B(i, j, k)] = -2;
+                    c++;
+                }
+            }
+        cntS[k] = c;
+    }
+    std::vector<long long> startS(nz + 3, 0);
+    startS[0] = nA;
+    for (int k = 1; k <= nz + 2; k++) startS[k] = startS[k - 1] + cntS[k - 1];
+    const long long nAct = startS[nz + 2];
+    if (nAct >= (1LL << 31) - 64) return fail(ctx, MFLBM_ERR_ARG, "too many active nodes");
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k <= nz + 1; k++) {
+        int n = (int)startS[k];
+        for (int j = 0; j <= ny + 1; j++)
+            for (int i = 0; i <= nx + 1; i++)
+                if (idx[B(i, j, k)] == -2) idx[B(i, j, k)] = n++;
+    }
+    // cell list and neighbour table
+    std::vector<int> cellA((size_t)nAct);
+    const int stride = (nA + 31) / 32 * 32;
+    std::vector<int> nbr((size_t)18 * (stride > 0 ? stride : 32), 0);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k <= nz + 1; k++)
+        for (int j = 0; j <= ny + 1; j++)
+            for (int i = 0; i <= nx + 1; i++) {
+                const int n = idx[B(i, j, k)];
+                if (n < 0) continue;
+                cellA[n] = g.cell(i, j, k);
+                if (n < nA)
+                    for (int q = 1; q < 19; q++) nbr[(size_t)(q - 1) * stride + n] = idx[B(i + EX(q), j + EY(q), k + EZ(q))];
+            }
+    d.nA = nA;
+    d.nAct = (int)nAct;
+    d.nbr_stride = stride > 0 ? stride : 32;
+    if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.nbr, nbr.size(), false) ||
+        dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))
+        return MFLBM_ERR_CUDA;
+    CU(cudaMemcpy(d.cellA, cellA.data(), (size_t)nAct * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.nbr, nbr.data(), nbr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    launch_fill_smap(ctx, ctx->s_main);
+    CU(cudaStreamSynchronize(ctx->s_main));
+    return 0;
+}
+
+// choose the population layout from the wall array and allocate the populations
+static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
+    Dev &d = ctx->d;
+    const Grid &g = d.g;
+    const mflbm_config &cfg = ctx->cfg;
+    int variant = cfg.kernel_variant;  // 0 auto, 1 dense, 2 sparse
+    if (cfg.porous_plate_cmd != 0) variant = 1;  // the porous plate copies from arbitrary (non-active) nodes
+    if (variant == 0) {
+        long long fluid = 0;
+#pragma omp parallel for reduction(+ : fluid) schedule(static)
+        for (int k = 1; k <= g.nz; k++)
+            for (int j = 1; j <= g.ny; j++)
+                for (int i = 1; i <= g.nx; i++)
+                    fluid += walls[(size_t)(i + 1) + (size_t)(g.nx + 4) * ((size_t)(j + 1) + (size_t)(g.ny + 4) * (size_t)(k + 1))] == 0;
+        const double porosity = (double)fluid / ((double)g.nx * g.ny * g.nz);
+        variant = porosity > 0.8 ? 1 : 2;
+    }
+    d.sparse = variant == 2;
+    d.full_curv = variant == 1;
+    size_t n = g.ntot;
+    if (d.sparse) {
+        if (build_active_set(ctx, walls)) return MFLBM_ERR_CUDA;
+        n = (size_t)d.nAct + 64;
+    }
+    for (int q = 0; q < 19; q++) {
+        if (dev_alloc(ctx, &d.f[q], n)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && dev_alloc(ctx, &d.gg[q], n)) return MFLBM_ERR_CUDA;
+    }
+    ctx->pdf_alloc = true;
+    return 0;
+}
+
 static int ensure_stage(mflbm_ctx *ctx, size_t bytes) {
     if (ctx->stage_bytes >= bytes) return 0;
     if (ctx->stage) cudaFree(ctx->stage);
+    for (int b = 0; b < 4; b++)
+        if (ctx->halo_buf[b]) cudaFree(ctx->halo_buf[b]);
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
     CU(cudaMalloc((void **)&ctx->stage, bytes));
@@ -302,15 +431,42 @@ static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, i
     return 0;
 }
 
+// one population array: caller's (0:nx+1,0:ny+1,0:nz+1) array <-> device (dense grid or active-node list).
+// Sparse download overwrites only the active entries of the caller's array: all other entries are never
+// touched by the reference either (they keep the values the caller's array already has).
+static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up) {
+    if (!host) return 0;
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "populations uploaded before the wall array");
+    const Grid &g = ctx->d.g;
+    if (!ctx->d.sparse) return xfer(ctx, dev, host, 1, g.nz + 2, 0, up);
+    const size_t n = (size_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
+    if (ensure_stage(ctx, n * sizeof(double))) return MFLBM_ERR_CUDA;
+    CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
+    launch_repack_sparse(ctx, ctx->s_main, dev, ctx->stage, up);
+    if (!up) CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
+    CU(cudaStreamSynchronize(ctx->s_main));
+    return 0;
+}
+
 extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
     if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
     Dev &d = ctx->d;
     const Grid &g = d.g;
     const int nz = g.nz;
+    if (h->walls) {
+        if (ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "the wall array can only be uploaded once per context");
+        const size_t n = (size_t)(g.nx + 4) * (g.ny + 4) * (nz + 4);
+        if (ensure_stage(ctx, n)) return MFLBM_ERR_CUDA;
+        CU(cudaMemcpyAsync(ctx->stage, h->walls, n, cudaMemcpyHostToDevice, ctx->s_main));
+        // cells outside the (-1:n+2) box keep walls=0 like an untouched allocation would; they are never read
+        launch_repack_i8(ctx, ctx->s_main, d.walls, (int8_t *)ctx->stage, 2, true);
+        CU(cudaStreamSynchronize(ctx->s_main));
+        if (setup_populations(ctx, h->walls)) return MFLBM_ERR_CUDA;
+    }
     for (int q = 0; q < 19; q++) {
-        if (xfer(ctx, d.f[q], h->f[q], 1, nz + 2, 0, true)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && xfer(ctx, d.gg[q], h->g[q], 1, nz + 2, 0, true)) return MFLBM_ERR_CUDA;
+        if (xfer_pdf(ctx, d.f[q], h->f[q], true)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], true)) return MFLBM_ERR_CUDA;
     }
     if (d.multiphase) {
         if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, true)) return MFLBM_ERR_CUDA;
@@ -323,14 +479,6 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
     }
     if (xfer(ctx, d.f_convec, h->f_convec_bc, 1, 19, -3, true)) return MFLBM_ERR_CUDA;
     if (xfer(ctx, d.w_in, h->w_in, 1, 1, -3, true)) return MFLBM_ERR_CUDA;
-    if (h->walls) {
-        const size_t n = (size_t)(g.nx + 4) * (g.ny + 4) * (nz + 4);
-        if (ensure_stage(ctx, n)) return MFLBM_ERR_CUDA;
-        CU(cudaMemcpyAsync(ctx->stage, h->walls, n, cudaMemcpyHostToDevice, ctx->s_main));
-        // cells outside the (-1:n+2) box keep walls=0 like an untouched allocation would; they are never read
-        launch_repack_i8(ctx, ctx->s_main, d.walls, (int8_t *)ctx->stage, 2, true);
-        CU(cudaStreamSynchronize(ctx->s_main));
-    }
     if (d.multiphase && h->solid_boundary_nodes && d.num_solid > 0) {
         std::vector<int> cell(d.num_solid);
         std::vector<unsigned> mask(d.num_solid);
@@ -382,8 +530,8 @@ extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
     const int nz = d.g.nz;
     CU(cudaStreamSynchronize(ctx->s_main));
     for (int q = 0; q < 19; q++) {
-        if (xfer(ctx, d.f[q], h->f[q], 1, nz + 2, 0, false)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && xfer(ctx, d.gg[q], h->g[q], 1, nz + 2, 0, false)) return MFLBM_ERR_CUDA;
+        if (xfer_pdf(ctx, d.f[q], h->f[q], false)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], false)) return MFLBM_ERR_CUDA;
     }
     if (d.multiphase) {
         if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, false)) return MFLBM_ERR_CUDA;
@@ -423,42 +571,51 @@ static int halo_exchange(mflbm_ctx *ctx, cudaStream_t st, bool push) {
     const bool has_hi = cfg.kper == 1 || cfg.idz != cfg.npz - 1;
     static const int qM[5] = {6, 14, 13, 18, 17}, qP[5] = {5, 11, 12, 15, 16};
     const size_t n = (size_t)g.sxy;
-    NC(ctx->nccl->GroupStart());
-    for (int fl = 0; fl < (d.multiphase ? 2 : 1); fl++) {
-        double *const *F = fl == 0 ? d.f : d.gg;
-        for (int m = 0; m < 5; m++) {
-            if (!push) {
-                if (has_lo) {
-                    NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(1), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-                    NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(0), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-                }
-                if (has_hi) {
-                    NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
-                    NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
-                }
-            } else {
-                if (has_lo) {
-                    NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(0), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-                    NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(1), n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-                }
-                if (has_hi) {
-                    NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
-                    NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, ctx->peer_hi, ctx->comm, st));
+    const int lo = ctx->peer_lo, hi = ctx->peer_hi;
+    // Issue order per message class: send(lo), send(hi), recv(hi), recv(lo).  With two ranks on a periodic ring both
+    // neighbours are the same peer and NCCL pairs sends and receives in issue order, so my "lo" message must meet
+    // the peer's "hi" receive.
+    if (d.sparse) {
+        const size_t nb = (size_t)(d.multiphase ? 10 : 5) * g.nx * g.ny;
+        for (int b = 0; b < 4; b++)
+            if (!ctx->halo_buf[b]) {
+                CU(cudaMalloc((void **)&ctx->halo_buf[b], nb * sizeof(double)));
+                ctx->bytes += (long long)(nb * sizeof(double));
+            }
+        double **hb = ctx->halo_buf;
+        launch_halo_pack(ctx, st, has_lo ? hb[0] : nullptr, has_hi ? hb[1] : nullptr, push, false);
+        NC(ctx->nccl->GroupStart());
+        if (has_lo) NC(ctx->nccl->Send(hb[0], nb, ncclDouble, lo, ctx->comm, st));
+        if (has_hi) NC(ctx->nccl->Send(hb[1], nb, ncclDouble, hi, ctx->comm, st));
+        if (has_hi) NC(ctx->nccl->Recv(hb[3], nb, ncclDouble, hi, ctx->comm, st));
+        if (has_lo) NC(ctx->nccl->Recv(hb[2], nb, ncclDouble, lo, ctx->comm, st));
+    } else {
+        NC(ctx->nccl->GroupStart());
+        for (int fl = 0; fl < (d.multiphase ? 2 : 1); fl++) {
+            double *const *F = fl == 0 ? d.f : d.gg;
+            for (int m = 0; m < 5; m++) {
+                if (!push) {
+                    if (has_lo) NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(1), n, ncclDouble, lo, ctx->comm, st));
+                    if (has_hi) NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, hi, ctx->comm, st));
+                    if (has_hi) NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, hi, ctx->comm, st));
+                    if (has_lo) NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(0), n, ncclDouble, lo, ctx->comm, st));
+                } else {
+                    if (has_lo) NC(ctx->nccl->Send(F[qP[m]] + g.plane_begin(0), n, ncclDouble, lo, ctx->comm, st));
+                    if (has_hi) NC(ctx->nccl->Send(F[qM[m]] + g.plane_begin(nz + 1), n, ncclDouble, hi, ctx->comm, st));
+                    if (has_hi) NC(ctx->nccl->Recv(F[qP[m]] + g.plane_begin(nz), n, ncclDouble, hi, ctx->comm, st));
+                    if (has_lo) NC(ctx->nccl->Recv(F[qM[m]] + g.plane_begin(1), n, ncclDouble, lo, ctx->comm, st));
                 }
             }
         }
     }
-    if (d.multiphase) {
-        if (has_lo) {
-            NC(ctx->nccl->Send(d.phi + g.plane_begin(1), 4 * n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-            NC(ctx->nccl->Recv(d.phi + g.plane_begin(-3), 4 * n, ncclDouble, ctx->peer_lo, ctx->comm, st));
-        }
-        if (has_hi) {
-            NC(ctx->nccl->Send(d.phi + g.plane_begin(nz - 3), 4 * n, ncclDouble, ctx->peer_hi, ctx->comm, st));
-            NC(ctx->nccl->Recv(d.phi + g.plane_begin(nz + 1), 4 * n, ncclDouble, ctx->peer_hi, ctx->comm, st));
-        }
+    if (d.multiphase) {  // phi stays on the dense grid in both layouts: four contiguous planes per direction
+        if (has_lo) NC(ctx->nccl->Send(d.phi + g.plane_begin(1), 4 * n, ncclDouble, lo, ctx->comm, st));
+        if (has_hi) NC(ctx->nccl->Send(d.phi + g.plane_begin(nz - 3), 4 * n, ncclDouble, hi, ctx->comm, st));
+        if (has_hi) NC(ctx->nccl->Recv(d.phi + g.plane_begin(nz + 1), 4 * n, ncclDouble, hi, ctx->comm, st));
+        if (has_lo) NC(ctx->nccl->Recv(d.phi + g.plane_begin(-3), 4 * n, ncclDouble, lo, ctx->comm, st));
     }
     NC(ctx->nccl->GroupEnd());
+    if (d.sparse) launch_halo_pack(ctx, st, has_lo ? ctx->halo_buf[2] : nullptr, has_hi ? ctx->halo_buf[3] : nullptr, push, true);
     return 0;
 }
 
@@ -470,6 +627,7 @@ static int check_launch(mflbm_ctx *ctx) {
 // main_iteration_kernel for one ntime
 static int step_impl(mflbm_ctx *ctx, int ntime) {
     const mflbm_config &cfg = ctx->cfg;
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_step before mflbm_upload");
     const int nz = cfg.nz;
     const bool odd = (ntime % 2) != 0;
     cudaStream_t s = ctx->s_main;

@@ -67,6 +67,17 @@ struct Dev {
     int *fluid_cell;
     double *fluid_nw;  // 5 doubles per node: nwx,nwy,nwz,cos(theta),sin(theta)
     int num_fluid;
+    // sparse storage of the populations (DESIGN.md "Sparse population storage"): the 38 PDF arrays hold only
+    // ACTIVE nodes = fluid nodes of 1..n (A, processed by the collision kernel, raster order k,j,i) followed by
+    // storage-only nodes (S: solid-boundary / ghost-plane nodes that are a D3Q19 neighbour of an A node).
+    // Scalar fields (phi, cn_*, c_norm, curv, walls, u,v,w,rho) stay on the dense padded grid.
+    int sparse;       // 0: PDFs on the dense grid, 1: PDFs on the active-node list
+    int nA, nAct;     // number of A nodes / of all active nodes
+    int nbr_stride;   // row stride of nbr (>= nA, multiple of 32)
+    int *cellA;       // [nAct] dense cell of each active node
+    int *nbr;         // [18][nbr_stride] active index of x+e_q for q=1..18 (row q-1), A nodes only
+    int *smap;        // [ntot] dense cell -> active index, -1 if not active
+    int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
     // scalars
     int multiphase, mrt;
     double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
@@ -102,11 +113,17 @@ struct mflbm_ctx {
     int peer_lo, peer_hi;  // ranks of z-1 / z+1 neighbours (periodic ring)
     bool open_z;
     bool macro_alloc;
+    bool pdf_alloc;
+    double *halo_buf[4];  // sparse NCCL exchange: send_lo, send_hi, recv_lo, recv_hi
+    std::vector<int> kstartA;  // sparse: first A index of plane k (k=1..nz+1), for slab launches
 };
 
 namespace mflbm {
 // launchers implemented in the .cu files
 void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1);
+void launch_fill_smap(mflbm_ctx *c, cudaStream_t st);
+void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev);
+void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack);
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);

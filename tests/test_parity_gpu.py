@@ -11,7 +11,9 @@ from helpers import compare_state, ctx_from_oracle, make_oracle
 
 pytestmark = pytest.mark.gpu
 
-TOL_STEP = 1e-12
+TOL_STEP = 1e-12   # FP64 relative, after one odd + one even step (FMA build)
+TOL_10 = 1e-9      # after ten steps: rounding differences are amplified through the normalised colour gradient
+LAYOUTS = [pytest.param(1, id="dense"), pytest.param(2, id="sparse")]
 
 
 def _run_both(o, ctx, nsteps, ntime0=1):
@@ -21,52 +23,57 @@ def _run_both(o, ctx, nsteps, ntime0=1):
     ctx.sync()
 
 
-@pytest.mark.parametrize("strict,tol", [(True, 0.0), (False, TOL_STEP)])
-def test_c1_tube_sphere_multiphase_steps(strict, tol):
-    """C1: 40x40x60 tube+sphere drainage, velocity inlet / convective outlet (BASELINE configs[0])."""
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fma"])
+def test_c1_tube_sphere_multiphase_steps(strict, layout):
+    """C1: 40x40x60 tube+sphere drainage, velocity inlet / convective outlet (BASELINE configs[0]).
+    strict (-fmad=false) build: bit-exact; default build: 1e-12 after 1 odd + 1 even step."""
     o = make_oracle(modify_geometry_cmd=1)
-    ctx = ctx_from_oracle(o, strict=strict)
+    ctx = ctx_from_oracle(o, strict=strict, kernel_variant=layout)
+    sp = layout == 2
     o.color_gradient()
     ctx.color_gradient()
-    compare_state(ctx, o, tol)
+    compare_state(ctx, o, 0.0 if strict else TOL_STEP, sparse=sp)
     t = 1
-    for nsteps in (1, 1, 8):  # one odd step, one even step, then eight more
+    for nsteps, tol in ((1, TOL_STEP), (1, TOL_STEP), (8, TOL_10)):  # one odd step, one even step, then eight more
         _run_both(o, ctx, nsteps, t)
         t += nsteps
-        compare_state(ctx, o, tol if strict else TOL_STEP * 10)
+        compare_state(ctx, o, 0.0 if strict else tol, sparse=sp)
     ctx.close()
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("inlet,outlet", [(2, 2), (1, 2)])
-def test_multiphase_pressure_bcs(inlet, outlet):
+def test_multiphase_pressure_bcs(inlet, outlet, layout):
     o = make_oracle(modify_geometry_cmd=1, inlet_BC=inlet, outlet_BC=outlet, force_z0=1e-5, sa_inject=0.8)
-    ctx = ctx_from_oracle(o, strict=True)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=layout)
     o.color_gradient(); ctx.color_gradient()
     _run_both(o, ctx, 6)
-    compare_state(ctx, o, 0.0)
+    compare_state(ctx, o, 0.0, sparse=layout == 2)
     ctx.close()
 
 
-def test_multiphase_periodic_z_bodyforce():
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_multiphase_periodic_z_bodyforce(layout):
     """z-periodic, body-force driven (the steady fractional-flow setup of test-suite case 5/6)."""
     rng = np.random.default_rng(5)
     wg = (rng.random((24, 20, 32)) < 0.2).astype(np.int8)
     o = make_oracle(nxG=24, nyG=20, nzG=32, kper=1, force_z0=2e-4, n_exclude_inlet=0, n_exclude_outlet=0,
                     initial_fluid_distribution_option=5, interface_z0=6.0, walls_global=wg, la_nu2=0.04)
-    ctx = ctx_from_oracle(o, strict=True)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=layout)
     o.color_gradient(); ctx.color_gradient()
     _run_both(o, ctx, 7)
-    compare_state(ctx, o, 0.0)
+    compare_state(ctx, o, 0.0, sparse=layout == 2)
     ctx.close()
 
 
 @pytest.mark.parametrize("mrt", [1, 3, 4])
 def test_multiphase_mrt_variants(mrt):
     o = make_oracle(modify_geometry_cmd=1, mrt=mrt)
-    ctx = ctx_from_oracle(o, strict=True)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=2)
     o.color_gradient(); ctx.color_gradient()
     _run_both(o, ctx, 4)
-    compare_state(ctx, o, 0.0)
+    compare_state(ctx, o, 0.0, sparse=True)
     ctx.close()
 
 
@@ -82,22 +89,24 @@ def test_porous_plate(plate):
 
 @pytest.mark.parametrize("cfg", [dict(kper=1, force_z0=1e-5), dict(inlet_BC=1, outlet_BC=1, Re=0.5, char_length=38.0),
                                  dict(inlet_BC=2, outlet_BC=2, rho_drop=1e-3)])
-def test_singlephase_steps(cfg):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_singlephase_steps(cfg, layout):
     rng = np.random.default_rng(7)
     wg = (rng.random((30, 26, 40)) < 0.25).astype(np.int8)
     wg[:, :, :4] = 0
     wg[:, :, -4:] = 0
     o = make_oracle(multiphase=0, nxG=30, nyG=26, nzG=40, la_nu1=0.1, walls_global=wg, n_exclude_inlet=0,
                     n_exclude_outlet=0, **cfg)
-    ctx = ctx_from_oracle(o, strict=True)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=layout)
     _run_both(o, ctx, 9)
-    compare_state(ctx, o, 0.0)
+    compare_state(ctx, o, 0.0, sparse=layout == 2)
     ctx.close()
 
 
-def test_monitors_match_oracle():
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_monitors_match_oracle(layout):
     o = make_oracle(modify_geometry_cmd=1)
-    ctx = ctx_from_oracle(o)
+    ctx = ctx_from_oracle(o, kernel_variant=layout)
     o.color_gradient(); ctx.color_gradient()
     v1, v2 = ctx.cal_saturation()
     s = o.cal_saturation()
@@ -113,8 +122,10 @@ def test_monitors_match_oracle():
     assert m["usq2"] == pytest.approx(mo["usq2"], rel=1e-10)
     got = ctx.download("u", "v", "w", "rho", "phi")
     for n in ("u", "v", "w", "rho", "phi"):
-        ref = o.field(n)
-        assert np.max(np.abs(got[n] - ref)) <= 1e-12 * np.max(np.abs(ref)), n
+        g_ = 3 if n == "phi" else 0  # compute_macro_vars covers 1..n only (ghost rho keeps the driver's init value)
+        a = got[n][1 + g_:-1 - g_, 1 + g_:-1 - g_, 1 + g_:-1 - g_]
+        ref = o.field(n)[1 + g_:-1 - g_, 1 + g_:-1 - g_, 1 + g_:-1 - g_]
+        assert np.max(np.abs(a - ref)) <= 1e-12 * np.max(np.abs(ref)), n
     assert ctx.monitor_breakthrough() == o.monitor_breakthrough()["outlet_phase1_sum"]
     c = ctx.monitor_steady_capillarypressure()
     co = o.monitor_steady_capillarypressure()

@@ -2,29 +2,9 @@
 //
 // Replaces color_gradient (MP/Phase_gradient.F90:5-204) and alter_color_gradient_solid_surface
 // (MP/Phase_gradient.F90:210-265): five launches K3..K7 exactly like the reference's five loop nests.
-#include "mflbm_internal.cuh"
+#include "gradient.cuh"
 
 namespace mflbm {
-
-#define ISO4_1 (1.0 / 6.0)
-#define ISO4_2 (1.0 / 12.0)
-
-// the three ISO4 central-difference shapes, terms in the reference's source order
-template <typename F>
-__device__ __forceinline__ double ddx(F v) {
-    return ISO4_1 * (v(1, 0, 0) - v(-1, 0, 0)) +
-           ISO4_2 * (v(1, 1, 0) - v(-1, -1, 0) + v(1, -1, 0) - v(-1, 1, 0) + v(1, 0, 1) - v(-1, 0, -1) + v(1, 0, -1) - v(-1, 0, 1));
-}
-template <typename F>
-__device__ __forceinline__ double ddy(F v) {
-    return ISO4_1 * (v(0, 1, 0) - v(0, -1, 0)) +
-           ISO4_2 * (v(1, 1, 0) - v(-1, -1, 0) + v(-1, 1, 0) - v(1, -1, 0) + v(0, 1, 1) - v(0, -1, -1) + v(0, 1, -1) - v(0, -1, 1));
-}
-template <typename F>
-__device__ __forceinline__ double ddz(F v) {
-    return ISO4_1 * (v(0, 0, 1) - v(0, 0, -1)) +
-           ISO4_2 * (v(1, 0, 1) - v(-1, 0, -1) + v(-1, 0, 1) - v(1, 0, -1) + v(0, 1, 1) - v(0, -1, -1) + v(0, -1, 1) - v(0, 1, -1));
-}
 
 __device__ __forceinline__ double w_equ(int n) { return n <= 6 ? 1.0 / 18.0 : 1.0 / 36.0; }
 
@@ -41,26 +21,41 @@ __global__ void k_phi_solid(const Dev P) {
     P.phi[c] = acc / P.solid_law[n];
 }
 
-// K4: ISO4 gradient of phi, norm, normalise; zero on walls / below 1e-6 (MP/Phase_gradient.F90:36-78)
-__global__ void __launch_bounds__(128) k_gradient(const Dev P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
-    const int j = (int)blockIdx.y - 1;
-    const int k = (int)blockIdx.z - 1;
-    if (i > P.g.nx + 2) return;
-    const int c = P.g.cell(i, j, k);
-    // solid nodes: the reference zeroes n and |grad phi| there every call; they are zero-initialised and only K6
-    // ever writes n at solid-boundary nodes (fully, after this kernel), so skipping the store is unobservable.
-    if (P.walls[c] == 1) return;
+// K4: ISO4 gradient of phi, norm, normalise; zero below 1e-6 (MP/Phase_gradient.F90:36-78).
+// Solid nodes: the reference zeroes n and |grad phi| there on every call; the arrays are zero-initialised and only K6
+// ever writes n at solid-boundary nodes (fully, after this kernel), so not touching solid nodes is unobservable.
+template <bool LAZY>
+__device__ __forceinline__ void gradient_at(const Dev &P, int c) {
     const int sx = P.g.sx, sxy = P.g.sxy;
     const double *__restrict__ ph = P.phi;
     auto v = [&](int a, int b, int d) { return ph[c + a + sx * b + sxy * d]; };
     const double gx = ddx(v), gy = ddy(v), gz = ddz(v);
     const double cn = sqrt(gx * gx + gy * gy + gz * gz);
     if (cn < 1e-6) {
+        // LAZY (sparse layout): bulk nodes already hold zeros; c_norm == 0 implies n == 0 at non-solid nodes
+        if (LAZY && P.c_norm[c] == 0.0) return;
         P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
     } else {
         P.cn_x[c] = gx / cn; P.cn_y[c] = gy / cn; P.cn_z[c] = gz / cn; P.c_norm[c] = cn;
     }
+}
+
+// dense traversal of the (-1:n+2)^3 box, like the reference's loop nest
+__global__ void __launch_bounds__(128) k_gradient(const Dev P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+    const int j = (int)blockIdx.y - 1;
+    const int k = (int)blockIdx.z - 1;
+    if (i > P.g.nx + 2) return;
+    const int c = P.g.cell(i, j, k);
+    if (P.walls[c] == 1) return;
+    gradient_at<false>(P, c);
+}
+
+// traversal of the list of non-solid cells of the same box (sparse layout: work scales with the pore space)
+__global__ void __launch_bounds__(128) k_gradient_list(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.nG) return;
+    gradient_at<true>(P, P.gcell[n]);
 }
 
 // K5: geometric wetting (Akai et al. 2018), MP/Phase_gradient.F90:225-261; cos/sin(theta) precomputed on the host
@@ -98,6 +93,19 @@ __global__ void k_cn_solid(const Dev P) {
     const unsigned m = P.solid_mask[n];
     if (!(m & 0x80000000u)) return;
     const int c = P.solid_cell[n];
+    if (P.sparse) {
+        // lazy path: if no listed fluid neighbour carries an interface (c_norm == 0 => n == 0) the result is exactly 0
+        bool any = false;
+#pragma unroll
+        for (int q = 1; q <= 18; q++)
+            if (m & (1u << q)) any |= (P.c_norm[c + P.g.off(q)] != 0.0);
+        if (!any) {
+            if (P.cn_x[c] != 0.0 || P.cn_y[c] != 0.0 || P.cn_z[c] != 0.0) {
+                P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0;
+            }
+            return;
+        }
+    }
     double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
     for (int q = 1; q <= 18; q++)
@@ -113,30 +121,24 @@ __global__ void k_cn_solid(const Dev P) {
     P.cn_z[c] = az / law;
 }
 
-// K7: curvature from the nine ISO4 derivatives of n, at all nodes incl. solids (MP/Phase_gradient.F90:116-200)
+// K7: curvature at all nodes incl. solids (MP/Phase_gradient.F90:116-200; the wall test at :121 is commented out).
+// On the sparse layout nothing consumes the curvature at solid nodes and the collision kernel evaluates it on the
+// fly, so this kernel only runs there when the field itself is requested (mflbm_download of curv).
 __global__ void __launch_bounds__(128) k_curvature(const Dev P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y + 1;
     const int k = blockIdx.z + 1;
     if (i > P.g.nx) return;
     const int c = P.g.cell(i, j, k);
-    // the reference evaluates the curvature at solid nodes too (MP/Phase_gradient.F90:121, test commented out);
-    // nothing on the hot path consumes it there, so it is only produced when full_curv is set.
     if (!P.full_curv && P.walls[c] != 0) return;
-    const int sx = P.g.sx, sxy = P.g.sxy;
-    const double *__restrict__ px = P.cn_x;
-    const double *__restrict__ py = P.cn_y;
-    const double *__restrict__ pz = P.cn_z;
-    auto vx = [&](int a, int b, int d) { return px[c + a + sx * b + sxy * d]; };
-    auto vy = [&](int a, int b, int d) { return py[c + a + sx * b + sxy * d]; };
-    auto vz = [&](int a, int b, int d) { return pz[c + a + sx * b + sxy * d]; };
-    const double kxx = ddx(vx), kyy = ddy(vy), kzz = ddz(vz);
-    const double kxy = ddy(vx), kxz = ddz(vx);
-    const double kyx = ddx(vy), kyz = ddz(vy);
-    const double kzx = ddx(vz), kzy = ddy(vz);
-    const double nx_ = px[c], ny_ = py[c], nz_ = pz[c];
-    P.curv[c] = (nx_ * nx_ - 1.0) * kxx + (ny_ * ny_ - 1.0) * kyy + (nz_ * nz_ - 1.0) * kzz + nx_ * ny_ * (kxy + kyx) +
-                nx_ * nz_ * (kxz + kzx) + ny_ * nz_ * (kzy + kyz);
+    P.curv[c] = curvature_at(P, c);
+}
+
+void launch_curvature(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    dim3 grid((P.g.nx + 127) / 128, P.g.ny, P.g.nz);
+    k_curvature<<<grid, 128, 0, st>>>(P);
+    c->launches++;
 }
 
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st) {
@@ -146,7 +148,12 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st) {
         k_phi_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
         c->launches++;
     }
-    {
+    if (P.sparse) {
+        if (P.nG > 0) {
+            k_gradient_list<<<(P.nG + 127) / 128, 128, 0, st>>>(P);
+            c->launches++;
+        }
+    } else {
         dim3 grid((P.g.nx + 4 + 127) / 128, P.g.ny + 4, P.g.nz + 4);
         k_gradient<<<grid, 128, 0, st>>>(P);
         c->launches++;
@@ -159,11 +166,7 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st) {
         k_cn_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
         c->launches++;
     }
-    {
-        dim3 grid((P.g.nx + 127) / 128, P.g.ny, P.g.nz);
-        k_curvature<<<grid, 128, 0, st>>>(P);
-        c->launches++;
-    }
+    if (!P.sparse) launch_curvature(c, st);  // sparse layout: evaluated inside the collision kernel
 }
 
 }  // namespace mflbm

@@ -5,7 +5,7 @@
 // (MP/Monitor.F90:27-85, SP/Monitor.F90:18-59), cal_saturation (MP/Monitor.F90:527-538),
 // monitor_breakthrough (:483-495), monitor_multiphase_steady_phasefield (:303-334) and
 // monitor_multiphase_steady_capillarypressure (:383-423).
-#include "mflbm_internal.cuh"
+#include "gradient.cuh"
 
 namespace mflbm {
 
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) k_macro(const Dev P) {
                 ft[14] + ft[15] + ft[16] + ft[17] + ft[18]) * (1 - wi);
     double fx = 0.0, fy = 0.0, fz = P.force_Z;
     if (MP) {
-        const double tmp = 0.5 * P.gamma * P.curv[c] * P.c_norm[c];
+        const double tmp = 0.5 * P.gamma * (SPARSE ? curvature_at(P, c) : P.curv[c]) * P.c_norm[c];
         fx = tmp * P.cn_x[c];
         fy = tmp * P.cn_y[c];
         fz = tmp * P.cn_z[c] + P.force_Z;

@@ -13,6 +13,7 @@
 //             step reads the 18 neighbour indices of the node (coalesced int32 rows).  Same 38 addresses are
 //             read and written per node, so the update stays race-free in any order, like the reference.
 #include "collide.cuh"
+#include "gradient.cuh"
 
 namespace mflbm {
 
@@ -56,7 +57,17 @@ __global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, in
     }
 
     if (MP) {
-        const double phi = collide_mp(P, a, b, P.cn_x[c], P.cn_y[c], P.cn_z[c], P.curv[c], P.c_norm[c]);
+        // c_norm == 0 (no interface nearby: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature) lets the sparse
+        // layout skip the normal loads and the curvature stencil.  Exact: the skipped terms are +-0.
+        const double c_norm = P.c_norm[c];
+        double cnx = 0.0, cny = 0.0, cnz = 0.0, curv = 0.0;
+        if (!SPARSE) {
+            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c]; curv = P.curv[c];
+        } else if (c_norm != 0.0) {
+            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
+            curv = curvature_at(P, c);  // K7 evaluated here from the neighbours' normals instead of a stored field
+        }
+        const double phi = collide_mp(P, a, b, cnx, cny, cnz, curv, c_norm);
         P.phi[c] = phi;
     } else {
         collide_sp(P, a);

@@ -339,6 +339,29 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
                 if (n < nA)
                     for (int q = 1; q < 19; q++) nbr[(size_t)(q - 1) * stride + n] = idx[B(i + EX(q), j + EY(q), k + EZ(q))];
             }
+    // G list: non-solid cells of the (-1:n+2)^3 box, raster order (where K4 evaluates the colour gradient)
+    std::vector<int> gcnt(nz + 5, 0);
+#pragma omp parallel for schedule(static)
+    for (int k = -1; k <= nz + 2; k++) {
+        int c = 0;
+        for (int j = -1; j <= ny + 2; j++)
+            for (int i = -1; i <= nx + 2; i++) c += (W(i, j, k) != 1);
+        gcnt[k + 2] = c;
+    }
+    std::vector<long long> gstart(nz + 6, 0);
+    for (int k = 0; k <= nz + 3; k++) gstart[k + 1] = gstart[k] + gcnt[k + 1];
+    const long long nG = gstart[nz + 4];
+    std::vector<int> gcell((size_t)(nG > 0 ? nG : 1));
+#pragma omp parallel for schedule(static)
+    for (int k = -1; k <= nz + 2; k++) {
+        long long n = gstart[k + 1];
+        for (int j = -1; j <= ny + 2; j++)
+            for (int i = -1; i <= nx + 2; i++)
+                if (W(i, j, k) != 1) gcell[n++] = g.cell(i, j, k);
+    }
+    d.nG = (int)nG;
+    if (dev_alloc(ctx, &d.gcell, gcell.size(), false)) return MFLBM_ERR_CUDA;
+    CU(cudaMemcpy(d.gcell, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
     d.nA = nA;
     d.nAct = (int)nAct;
     d.nbr_stride = stride > 0 ? stride : 32;
@@ -534,6 +557,10 @@ extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], false)) return MFLBM_ERR_CUDA;
     }
     if (d.multiphase) {
+        if (d.sparse && h->curv) {  // not maintained per step on the sparse layout: evaluate K7 now (fluid nodes)
+            launch_curvature(ctx, ctx->s_main);
+            CU(cudaGetLastError());
+        }
         if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, false)) return MFLBM_ERR_CUDA;
         if (xfer(ctx, d.phi_old, h->phi_old, 4, nz + 8, -3, false)) return MFLBM_ERR_CUDA;
         if (xfer(ctx, d.cn_x, h->cn_x, 2, nz + 4, -1, false) || xfer(ctx, d.cn_y, h->cn_y, 2, nz + 4, -1, false) ||

@@ -77,6 +77,8 @@ struct Dev {
     int *cellA;       // [nAct] dense cell of each active node
     int *nbr;         // [18][nbr_stride] active index of x+e_q for q=1..18 (row q-1), A nodes only
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
+    int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
+    int nG;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
     // scalars
     int multiphase, mrt;
@@ -125,6 +127,7 @@ void launch_fill_smap(mflbm_ctx *c, cudaStream_t st);
 void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev);
 void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack);
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st);
+void launch_curvature(mflbm_ctx *c, cudaStream_t st);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
 void launch_macro(mflbm_ctx *c, cudaStream_t st);

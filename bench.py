@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the MF-LBM time-step hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, z-slab decomposition, weak scaling)
+
+One "step" = one call of main_iteration_kernel (mflbm_step): collision+streaming of every fluid node, halo exchange,
+inlet/outlet kernels and colour gradient.  MLUPS counts fluid (pore) nodes only, like the reference's benchmark
+(MP/Main_multiphase.F90:540).  Default workload at N=1: BASELINE.json configs[2], the multiphase 512^3 sphere-pack
+drainage (the largest single-GPU configuration of the headline, multiphase, metric); N>1 stacks one such 512^3 slab
+per GPU along z (weak scaling).  ``--workload c2`` is configs[1] (singlephase 240^3 Bentheimer-like, periodic z).
+
+The GPU arm never touches oracle/: geometry, node lists and initial fields come from the host driver mirror
+(mf-lbm_b200/host), everything per step from libmflbm.so through the C ABI.  The CPU oracle is only executed for
+the ``cpu_baseline`` figure and for ``--impl reference``.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE = {True: 624.0, False: 304.0}  # (38+38) PDFs + phi write + phi read ; (19+19) PDFs
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_spec(name, n_gpus):
+    """Control-file overrides + geometry recipe for each BASELINE.json config."""
+    if name == "c3":  # configs[2] (N=1) / weak-scaling stack (N>1), SURVEY 8(d) C3/C5 physics
+        n = int(os.environ.get("MFLBM_BENCH_N", "512"))
+        return dict(multiphase=True, nx=n, ny=n, nz=n * n_gpus, periodic=False,
+                    geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=1, buffer=10),
+                    control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
+                                 RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
+                                 initial_interface_position=8.0, initial_fluid_distribution_option=1,
+                                 excluded_layers="10,10"),
+                    label="multiphase_3D scCO2/brine drainage, synthetic random-sphere-pack %dx%dx%d (porosity 0.36, "
+                          "10 buffer layers each end), velocity inlet / convective outlet" % (n, n, n * n_gpus))
+    if name == "c2":  # configs[1]
+        n = int(os.environ.get("MFLBM_BENCH_N", "240"))
+        return dict(multiphase=False, nx=n, ny=n, nz=(n + 20) * n_gpus, periodic=True,
+                    geometry=dict(porosity=0.18, rmin=6.0, rmax=14.0, seed=20261017, buffer=10),
+                    control=dict(fluid_viscosity=0.1, body_force_0="1d-5", MRT_collision_parameter_preset=1,
+                                 periodic_indicator="0,0,1", excluded_layers="10,10"),
+                    label="singlephase_3D absolute-permeability run, Bentheimer-like synthetic %dx%dx%d wall array "
+                          "(porosity 0.18 core + 10 fluid layers each end), periodic z, body force" % (n, n, (n + 20) * n_gpus))
+    if name == "c1":  # configs[0]: the reference's own CPU-runnable case
+        return dict(multiphase=True, nx=40, ny=40, nz=60 * n_gpus, periodic=False, geometry=None,
+                    control=dict(modify_geometry_cmd=1, breakthrough_check=1),
+                    label="test_suites/3D_simulation tube-with-sphere drainage 40x40x%d" % (60 * n_gpus))
+    raise SystemExit("unknown workload " + name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def cpu_reference_run(spec, steps, warmup, sample_n=None):
+    """The reference's CPU implementation of the path = the C/OpenMP oracle (the Fortran cannot be built in this image:
+    no gfortran / mpif90), timing build, all host threads, on a bounded sample of the same workload."""
+    from oracle.oracle import Oracle, default_params
+    import mflbm_b200 as M
+    from importlib import import_module
+    geo = import_module("mflbm_b200.geometry")
+    mp = spec["multiphase"]
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if spec["geometry"] is None:
+        n, nz = spec["nx"], spec["nz"]
+        walls = None
+    else:
+        n = sample_n or (128 if mp else 160)
+        nz = n
+        walls = geo.sphere_pack(n, n, nz, periodic=spec["periodic"], **spec["geometry"])
+    c = spec["control"]
+    fl = lambda v: float(str(v).replace("d", "e"))
+    kw = dict(multiphase=1 if mp else 0, nxG=n, nyG=n, nzG=nz)
+    if mp:
+        kw.update(la_nu1=fl(c.get("fluid1_viscosity", 0.004)), la_nu2=fl(c.get("fluid2_viscosity", 0.4)), gamma=fl(c.get("surface_tension", 0.03)),
+                  theta_deg=fl(c.get("theta", 30)), beta=fl(c.get("RK_beta", 0.95)), ca_0=fl(c.get("capillary_number", "100d-6")),
+                  modify_geometry_cmd=int(c.get("modify_geometry_cmd", 0)))
+    else:
+        kw.update(la_nu1=fl(c["fluid_viscosity"]), force_z0=fl(c["body_force_0"]), kper=1, inlet_BC=0, outlet_BC=0,
+                  n_exclude_inlet=10, n_exclude_outlet=10)
+    o = Oracle(default_params(**kw), fast=True)
+    o.setup(walls)
+    if mp:
+        o.color_gradient()
+    pore = o.get_i64("pore_sum")
+    for t in range(1, warmup + 1):
+        o.step(t)
+    t0 = time.perf_counter()
+    for t in range(warmup + 1, warmup + steps + 1):
+        o.step(t)
+    dt = time.perf_counter() - t0
+    mlups = pore * steps / dt / 1e6
+    return dict(value=mlups, ms_per_step=dt / steps * 1e3, cores=cores, pore=int(pore),
+                sample="%s %dx%dx%d sample of the same medium/physics, %d timed steps, OpenMP %d threads, gcc -O3" % (
+                    "multiphase" if mp else "singlephase", n, n, nz, steps, cores))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 dense, 2 sparse")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps % 2:
+        args.steps += 1  # AA pattern: keep odd/even parity across rounds like the reference (MP/Main_multiphase.F90:510)
+    if args.warmup % 2:
+        args.warmup += 1
+    args.warmup = max(args.warmup, 4)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = world if world > 1 else 1
+    spec = workload_spec(args.workload, n_gpus)
+    mp = spec["multiphase"]
+    bpu = BYTES_PER_UPDATE[mp]
+    peak, peak_src = measured_peaks()
+
+    # ------------------------------------------------------------------ reference arm (CPU) ----------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(workload_spec(args.workload, 1), max(2, min(args.steps, 20)), max(2, min(args.warmup, 4)))
+        print(json.dumps({
+            "impl": "reference", "metric": "MLUPS", "value": r["value"], "unit": "MLUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": spec["label"], "note": "reference Fortran cannot be compiled here (no gfortran/mpif90); "
+                       "this arm times the C/OpenMP port of its CPU path (oracle/) on a bounded sample"},
+            "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm -------------------------------
+    import torch
+    import mflbm_b200 as M
+    from importlib import import_module
+    geo = import_module("mflbm_b200.geometry")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def allreduce(x, op="sum"):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nx, ny, nzG = spec["nx"], spec["ny"], spec["nz"]
+    nz = nzG // n_gpus
+    t_setup = time.time()
+    tmp = tempfile.mkdtemp(prefix="mflbm_bench_")
+    ctl = M.write_control_file(os.path.join(tmp, "simulation_control.txt"), multiphase=mp,
+                               lattice_dimensions="%d,%d,%d" % (nx, ny, nzG), MPI_process_num="1,1,%d" % n_gpus,
+                               MPI_async_layers_num="0,0,4", external_geometry_read_cmd=0 if spec["geometry"] is None else 1,
+                               **spec["control"])
+    if spec["geometry"] is None:
+        drv = M.Driver(ctl, idz=rank, lazy_pdfs=True)
+    else:
+        k0, k1 = M.Driver.window_range(rank, n_gpus, nzG, spec["periodic"]) if n_gpus > 1 else (1, nzG)
+        w = geo.sphere_pack_window(nx, ny, nzG, k0, k1, periodic=spec["periodic"], **spec["geometry"])
+        drv = M.Driver(ctl, idz=rank, walls_window=(w, k0), lazy_pdfs=True)
+        del w
+    drv.setup()
+    pore_local = drv.i64("pore_sum_local")
+    pore_global = int(round(allreduce(float(pore_local))))
+    drv.set_pore_sum(pore_global)
+    nccl_id = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(M.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+    drv.create_context(device=local_rank, nccl_unique_id=nccl_id, kernel_variant=args.variant)
+    drv.upload(free_host=True)
+    if mp:
+        drv.color_gradient()
+    drv.sync()
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        drv.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # warm-up
+    drv.run(1, args.warmup)
+    barrier()
+    launches0 = drv.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    drv.profile(True)
+    # timed region: EXACTLY args.steps steps, device-timed (CUDA events on the compute stream), max over ranks
+    barrier()
+    drv.timer_start()
+    drv.run(1, args.steps)
+    ms = drv.timer_stop()
+    barrier()
+    coll_ms, coll_launches = drv.profile_read()
+    drv.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = drv.launch_count - launches0
+    ms = allreduce(ms, "max")
+    mlups = pore_global * args.steps / (ms * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (k_collide): algorithmic bytes of the launches / their event-timed duration
+    coll_bytes = bpu * pore_local * args.steps
+    achieved = coll_bytes / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+
+    # e2e through the C ABI with HOST buffers: per step H2D of the step's host input (inlet profile w_in, pinned),
+    # mflbm_step, and a D2H read of the step's result (saturation partial sums via mflbm_cal_saturation / flow monitor)
+    w_in = torch.zeros((ny + 2) * (nx + 2), dtype=torch.float64).pin_memory()
+    w_in.copy_(torch.from_numpy(np.ascontiguousarray(drv.field("w_in").ravel(order="F"))))
+    e2e_steps = args.steps
+    barrier()
+    t0 = time.perf_counter()
+    drv.timer_start()
+    acc = 0.0
+    for t in range(1, e2e_steps + 1):
+        drv.upload_w_in(w_in.data_ptr())
+        drv.main_iteration_kernel(t)
+        if mp:
+            v1, v2 = drv.cal_saturation_parts()
+            acc += v1
+        else:
+            drv.sync()
+    ms_e2e = drv.timer_stop()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = allreduce(max(ms_e2e, 0.0), "max")
+    e2e_mlups = pore_global * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    h2d = (nx + 2) * (ny + 2) * 8
+    d2h = 2 * nz * 8 if mp else 0
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": spec["label"], "fluid_nodes": pore_global, "porosity": pore_global / float(nx * ny * nzG),
+                       "per_gpu_lattice": "%dx%dx%d" % (nx, ny, nz), "parallelism": "z-slab x%d" % n_gpus,
+                       "l2_policy": "working set per step (%.1f GB) >> 126 MB L2, no flush needed" % (drv.device_bytes / 1e9),
+                       "population_layout": "auto (kernel_variant=%d)" % args.variant, "setup_s": round(setup_s, 1),
+                       "device_bytes_per_gpu": drv.device_bytes},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_collide (collision + AA streaming)", "peak_source": peak_src,
+                         "bytes_per_update": bpu, "kernel_ms_per_step": coll_ms / args.steps, "kernel_launches": coll_launches,
+                         "step_frac_of_roofline": mlups * 1e6 * bpu / 1e9 / (peak * n_gpus)},
+            "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / e2e_steps, "host_wall_ms_per_step": wall_e2e / e2e_steps,
+                    "what": "per step: mflbm_upload(w_in, pinned host) + mflbm_step + mflbm_cal_saturation read-back"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    drv.close()
+    if rank == 0:
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(workload_spec(args.workload, 1), 10 if mp else 20, 2)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -139,6 +139,13 @@ int mflbm_sync(mflbm_ctx *ctx);
 int mflbm_timer_start(mflbm_ctx *ctx);
 int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms); /* CUDA-event time on the compute stream */
 
+/* Per-kernel device timing of the dominant kernel (collision + streaming) for the roofline report: while enabled,
+ * every launch of it is bracketed by CUDA events on its own stream.  mflbm_profile_read synchronises, returns the
+ * accumulated kernel time and launch count since the last read, and resets the counters.  The analogue of the
+ * reference's -Dgpu_profiling cudaProfilerStart/Stop bracket (MP/Main_multiphase.F90:525-533). */
+int mflbm_profile(mflbm_ctx *ctx, int enable);
+int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long *collide_launches);
+
 /* kernel launches issued by this context since create (bench.py "gpu_launches") */
 long long mflbm_launch_count(const mflbm_ctx *ctx);
 /* algorithmic device bytes held by the context */

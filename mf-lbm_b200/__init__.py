@@ -6,3 +6,4 @@ The directory name contains a hyphen, so import it through the root-level shim `
 """
 from .binding import (Config, Arrays, Context, MflbmError, EXPORTS, SOLID_DTYPE, FLUID_DTYPE,  # noqa: F401
                       SOLVER_MULTIPHASE, SOLVER_SINGLEPHASE, build, load, nccl_unique_id, field_shape)
+from .driver import Driver, write_control_file, write_wall_array, build_host, load_host  # noqa: F401,E402

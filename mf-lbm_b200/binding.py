@@ -48,7 +48,7 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_step", "mflbm_run", "mflbm_color_gradient", "mflbm_compute_macro_vars", "mflbm_monitor",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
-           "mflbm_timer_stop", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id")
+           "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id")
 
 
 class MflbmError(RuntimeError):
@@ -96,6 +96,8 @@ def load(strict=False):
     lib.mflbm_sync.argtypes = [vp]
     lib.mflbm_timer_start.argtypes = [vp]
     lib.mflbm_timer_stop.argtypes = [vp, _DP]
+    lib.mflbm_profile.argtypes = [vp, C.c_int]
+    lib.mflbm_profile_read.argtypes = [vp, _DP, C.POINTER(C.c_longlong)]
     lib.mflbm_launch_count.argtypes = [vp]
     lib.mflbm_launch_count.restype = C.c_longlong
     lib.mflbm_device_bytes.argtypes = [vp]
@@ -285,6 +287,14 @@ class Context:
         ms = C.c_double()
         self._chk(self.lib.mflbm_timer_stop(self.h, C.byref(ms)), "mflbm_timer_stop")
         return ms.value
+
+    def profile(self, enable):
+        self._chk(self.lib.mflbm_profile(self.h, int(enable)), "mflbm_profile")
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_longlong()
+        self._chk(self.lib.mflbm_profile_read(self.h, C.byref(ms), C.byref(n)), "mflbm_profile_read")
+        return ms.value, n.value
 
     @property
     def launch_count(self):

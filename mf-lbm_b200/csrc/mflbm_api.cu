@@ -145,6 +145,10 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->comm = nullptr;
     ctx->macro_alloc = false;
     ctx->pdf_alloc = false;
+    ctx->prof = false;
+    ctx->prof_used = 0;
+    ctx->prof_ms = 0;
+    ctx->prof_launches = 0;
     ctx->halo_buf[0] = ctx->halo_buf[1] = ctx->halo_buf[2] = ctx->halo_buf[3] = nullptr;
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
@@ -253,6 +257,7 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -651,6 +656,38 @@ static int check_launch(mflbm_ctx *ctx) {
     return 0;
 }
 
+// flush recorded event pairs into the accumulated collision-kernel time
+static int prof_flush(mflbm_ctx *ctx) {
+    for (size_t n = 0; n + 1 < ctx->prof_used; n += 2) {
+        CU(cudaEventSynchronize(ctx->prof_ev[n + 1]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->prof_ev[n], ctx->prof_ev[n + 1]));
+        ctx->prof_ms += ms;
+        ctx->prof_launches++;
+    }
+    ctx->prof_used = 0;
+    return 0;
+}
+
+static int collide_timed(mflbm_ctx *ctx, cudaStream_t s, bool odd, int k0, int k1) {
+    if (!ctx->prof) {
+        launch_collide(ctx, s, odd, k0, k1);
+        return 0;
+    }
+    if (ctx->prof_used + 2 > 4096 && prof_flush(ctx)) return MFLBM_ERR_CUDA;
+    while (ctx->prof_ev.size() < ctx->prof_used + 2) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->prof_ev.push_back(e);
+    }
+    const long long before = ctx->launches;
+    CU(cudaEventRecord(ctx->prof_ev[ctx->prof_used], s));
+    launch_collide(ctx, s, odd, k0, k1);
+    CU(cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], s));
+    if (ctx->launches > before) ctx->prof_used += 2;
+    return 0;
+}
+
 // main_iteration_kernel for one ntime
 static int step_impl(mflbm_ctx *ctx, int ntime) {
     const mflbm_config &cfg = ctx->cfg;
@@ -662,16 +699,15 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
         // boundary slabs first, exchange on the high-priority halo stream while the interior runs
         // (MP/Main_multiphase.F90:358-387, :423-458)
         const int iz = cfg.iz_async > 0 ? cfg.iz_async : 1;
-        launch_collide(ctx, s, odd, 1, iz);
-        launch_collide(ctx, s, odd, nz - iz + 1, nz);
+        if (collide_timed(ctx, s, odd, 1, iz) || collide_timed(ctx, s, odd, nz - iz + 1, nz)) return MFLBM_ERR_CUDA;
         CU(cudaEventRecord(ctx->ev_slab, s));
         CU(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_slab, 0));
         if (halo_exchange(ctx, ctx->s_halo, odd)) return MFLBM_ERR_NCCL;
         CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
-        launch_collide(ctx, s, odd, iz + 1, nz - iz);
+        if (collide_timed(ctx, s, odd, iz + 1, nz - iz)) return MFLBM_ERR_CUDA;
         CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
     } else {
-        launch_collide(ctx, s, odd, 1, nz);
+        if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
         if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
     }
     launch_bc(ctx, s, odd);
@@ -846,6 +882,23 @@ extern "C" int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
     *elapsed_ms = ms;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_profile(mflbm_ctx *ctx, int enable) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    if (prof_flush(ctx)) return MFLBM_ERR_CUDA;
+    ctx->prof = enable != 0;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long *collide_launches) {
+    if (!ctx || !collide_ms || !collide_launches) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    if (prof_flush(ctx)) return MFLBM_ERR_CUDA;
+    *collide_ms = ctx->prof_ms;
+    *collide_launches = ctx->prof_launches;
+    ctx->prof_ms = 0;
+    ctx->prof_launches = 0;
     return MFLBM_OK;
 }
 

@@ -117,7 +117,12 @@ struct mflbm_ctx {
     bool macro_alloc;
     bool pdf_alloc;
     double *halo_buf[4];  // sparse NCCL exchange: send_lo, send_hi, recv_lo, recv_hi
-    std::vector<int> kstartA;  // sparse: first A index of plane k (k=1..nz+1), for slab launches
+    std::vector<int> kstartA;
+    bool prof;                         // per-launch event timing of the collision kernel
+    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+    size_t prof_used;
+    double prof_ms;
+    long long prof_launches;  // sparse: first A index of plane k (k=1..nz+1), for slab launches
 };
 
 namespace mflbm {

@@ -67,9 +67,11 @@ public:
     double force_Z = 0, rho_in = 1, rho_out = 1, relaxation = 1, uin_avg = 0, uin_avg_0 = 0, flowrate = 0;
     double s_e = 0, s_e2 = 0, s_q = 0, s_nu = 0, s_pi = 0, s_t = 0;
     long long pore_sum = 0, pore_sum_effective = 0;
-    std::vector<int> pore_profile_z;  // global profile (1:nzGlobal)
+    std::vector<int> pore_profile_z;  // profile over the planes held in walls_global (index k - wk0)
     // geometry
-    std::vector<int8_t> walls_global;  // (1:nxG,1:nyG,1:nzG)
+    std::vector<int8_t> walls_global;  // (1:nxG,1:nyG,wk0:wk1): the whole lattice, or a z window around this slab
+    int wk0 = 1, wk1 = 0;              // global plane range held in walls_global (wk1 < wk0: not set -> whole lattice)
+    long long pore_sum_local = 0;      // fluid nodes of this slab
     std::vector<int8_t> walls;         // (-1:n+2)^3
     std::vector<mflbm_solid_node> solid_boundary_nodes;
     std::vector<mflbm_fluid_node> fluid_boundary_nodes;
@@ -77,6 +79,7 @@ public:
     // fields handed to mflbm_upload
     std::vector<double> f[19], g[19], phi, w_in, f_convec_bc, g_convec_bc, phi_convec_bc;
     // device context
+    bool lazy_pdfs = false;  // true: populations are generated one array at a time during upload (large lattices)
     mflbm_ctx *ctx = nullptr;
     std::string error;
 
@@ -100,6 +103,9 @@ public:
     bool monitor(int ntime, MonitorResult *out, const std::string &outdir);  // MP/Monitor.F90:5-277 (np==1 tail)
     bool cal_saturation(double *saturation_full_domain);                     // MP/Monitor.F90:512-550
     bool benchmark(int warmup, int rounds, int steps, double *best_mlups, double *ms_per_step);  // MP/Main_multiphase.F90:498-556
+
+    double pdf_value(int i, int j, int k, int q, int fluid) const;
+    void fill_pdf(std::vector<double> &a, int q, int fluid) const;
 
 private:
     void inlet_vel_profile_rectangular(double vel_avg, int num_terms);  // MP/Misc.F90:625-665

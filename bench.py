@@ -278,6 +278,7 @@ def main():
     drv.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     launches = drv.launch_count - launches0
+    ntile, nquiet = drv.tile_stats()
     ms = allreduce(ms, "max")
     mlups = pore_global * args.steps / (ms * 1e-3) / 1e6
 
@@ -324,7 +325,8 @@ def main():
                        "per_gpu_lattice": "%dx%dx%d" % (nx, ny, nz), "parallelism": "z-slab x%d" % n_gpus,
                        "l2_policy": "working set per step (%.1f GB) >> 126 MB L2, no flush needed" % (drv.device_bytes / 1e9),
                        "population_layout": "auto (kernel_variant=%d)" % args.variant, "setup_s": round(setup_s, 1),
-                       "device_bytes_per_gpu": drv.device_bytes},
+                       "device_bytes_per_gpu": drv.device_bytes,
+                       "quiet_tile_fraction": (nquiet / ntile) if ntile else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_collide (collision + AA streaming)", "peak_source": peak_src,
                          "bytes_per_update": bpu, "kernel_ms_per_step": coll_ms / args.steps, "kernel_launches": coll_launches,

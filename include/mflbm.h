@@ -146,6 +146,11 @@ int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms); /* CUDA-event time on 
 int mflbm_profile(mflbm_ctx *ctx, int enable);
 int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long *collide_launches);
 
+/* Quiet-tile statistics of the sparse multiphase layout (DESIGN.md "Quiet tiles"): number of 8x4x4-cell tiles and how
+ * many of them the last gradient chain skipped because phi is uniform around them.  Informational (bench.py reports
+ * the fraction; tests use it to make sure the skipping path is exercised); 0/0 when the layout has no tiles. */
+int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nquiet);
+
 /* kernel launches issued by this context since create (bench.py "gpu_launches") */
 long long mflbm_launch_count(const mflbm_ctx *ctx);
 /* algorithmic device bytes held by the context */

@@ -48,7 +48,8 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_step", "mflbm_run", "mflbm_color_gradient", "mflbm_compute_macro_vars", "mflbm_monitor",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
-           "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id")
+           "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
+           "mflbm_tile_stats")
 
 
 class MflbmError(RuntimeError):
@@ -98,6 +99,7 @@ def load(strict=False):
     lib.mflbm_timer_stop.argtypes = [vp, _DP]
     lib.mflbm_profile.argtypes = [vp, C.c_int]
     lib.mflbm_profile_read.argtypes = [vp, _DP, C.POINTER(C.c_longlong)]
+    lib.mflbm_tile_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.mflbm_launch_count.argtypes = [vp]
     lib.mflbm_launch_count.restype = C.c_longlong
     lib.mflbm_device_bytes.argtypes = [vp]
@@ -295,6 +297,12 @@ class Context:
         ms, n = C.c_double(), C.c_longlong()
         self._chk(self.lib.mflbm_profile_read(self.h, C.byref(ms), C.byref(n)), "mflbm_profile_read")
         return ms.value, n.value
+
+    def tile_stats(self):
+        """(number of tiles, number of quiet tiles) of the last gradient chain; (0, 0) without tiles"""
+        a, b = C.c_longlong(), C.c_longlong()
+        self._chk(self.lib.mflbm_tile_stats(self.h, C.byref(a), C.byref(b)), "mflbm_tile_stats")
+        return a.value, b.value
 
     @property
     def launch_count(self):

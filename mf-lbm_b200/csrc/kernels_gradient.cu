@@ -8,10 +8,13 @@ namespace mflbm {
 
 __device__ __forceinline__ double w_equ(int n) { return n <= 6 ? 1.0 / 18.0 : 1.0 / 36.0; }
 
+// ---------------------------------------------------------------------------------------------------
+// Per-entry device functions of the five loop nests; the launch shapes below (raster lists / dense loops for the
+// reference-order variant, tile-driven for the sparse layout) only differ in how entries are enumerated.
+// ---------------------------------------------------------------------------------------------------
+
 // K3: phi on solid boundary nodes = weighted mean over listed fluid neighbours (MP/Phase_gradient.F90:16-29)
-__global__ void k_phi_solid(const Dev P) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P.num_solid) return;
+__device__ __forceinline__ void phi_solid_at(const Dev &P, int n) {
     const int c = P.solid_cell[n];
     const unsigned m = P.solid_mask[n];
     double acc = 0.0;
@@ -40,28 +43,8 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
     }
 }
 
-// dense traversal of the (-1:n+2)^3 box, like the reference's loop nest
-__global__ void __launch_bounds__(128) k_gradient(const Dev P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
-    const int j = (int)blockIdx.y - 1;
-    const int k = (int)blockIdx.z - 1;
-    if (i > P.g.nx + 2) return;
-    const int c = P.g.cell(i, j, k);
-    if (P.walls[c] == 1) return;
-    gradient_at<false>(P, c);
-}
-
-// traversal of the list of non-solid cells of the same box (sparse layout: work scales with the pore space)
-__global__ void __launch_bounds__(128) k_gradient_list(const Dev P) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P.nG) return;
-    gradient_at<true>(P, P.gcell[n]);
-}
-
 // K5: geometric wetting (Akai et al. 2018), MP/Phase_gradient.F90:225-261; cos/sin(theta) precomputed on the host
-__global__ void k_alter(const Dev P) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P.num_fluid) return;
+__device__ __forceinline__ void alter_at(const Dev &P, int n) {
     const int c = P.fluid_cell[n];
     if (!(P.c_norm[c] > 1e-6)) return;
     const double nwx = P.fluid_nw[5 * n + 0], nwy = P.fluid_nw[5 * n + 1], nwz = P.fluid_nw[5 * n + 2];
@@ -87,9 +70,7 @@ __global__ void k_alter(const Dev P) {
 }
 
 // K6: normal on solid boundary nodes inside the 0..n+1 box (MP/Phase_gradient.F90:88-109)
-__global__ void k_cn_solid(const Dev P) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P.num_solid) return;
+__device__ __forceinline__ void cn_solid_at(const Dev &P, int n) {
     const unsigned m = P.solid_mask[n];
     if (!(m & 0x80000000u)) return;
     const int c = P.solid_cell[n];
@@ -121,6 +102,39 @@ __global__ void k_cn_solid(const Dev P) {
     P.cn_z[c] = az / law;
 }
 
+// ---- raster launch shapes (dense layout, sparse layout without tiles) ----
+__global__ void k_phi_solid(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.num_solid) phi_solid_at(P, n);
+}
+
+// dense traversal of the (-1:n+2)^3 box, like the reference's loop nest
+__global__ void __launch_bounds__(128) k_gradient(const Dev P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+    const int j = (int)blockIdx.y - 1;
+    const int k = (int)blockIdx.z - 1;
+    if (i > P.g.nx + 2) return;
+    const int c = P.g.cell(i, j, k);
+    if (P.walls[c] == 1) return;
+    gradient_at<false>(P, c);
+}
+
+// traversal of the list of non-solid cells of the same box (sparse layout: work scales with the pore space)
+__global__ void __launch_bounds__(128) k_gradient_list(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.nG) gradient_at<true>(P, P.gcell[n]);
+}
+
+__global__ void k_alter(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.num_fluid) alter_at(P, n);
+}
+
+__global__ void k_cn_solid(const Dev P) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.num_solid) cn_solid_at(P, n);
+}
+
 // K7: curvature at all nodes incl. solids (MP/Phase_gradient.F90:116-200; the wall test at :121 is commented out).
 // On the sparse layout nothing consumes the curvature at solid nodes and the collision kernel evaluates it on the
 // fly, so this kernel only runs there when the field itself is requested (mflbm_download of curv).
@@ -141,9 +155,209 @@ void launch_curvature(mflbm_ctx *c, cudaStream_t st) {
     c->launches++;
 }
 
-void launch_color_gradient(mflbm_ctx *c, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------------
+// Quiet tiles (sparse multiphase layout).  Exactness argument (DESIGN.md "Quiet tiles"): the ISO4 gradient of values
+// that all lie within +-1e-7 of the same constant is below 1.8e-7 < 1e-6, which the reference zeroes
+// (MP/Phase_gradient.F90:64-73); tiles are at least 4 cells wide, so every phi value that can influence K3..K7 at a
+// cell of tile T (radius 3) lies in T's 27-tile neighbourhood.  A tile turns quiet only after one full evaluation
+// under uniform phi (two consecutive steps with the same single class), which leaves n = |grad phi| = 0 stored.
+// The node lists are sorted by tile at upload (CSR ranges t*_start), so the chain only touches ACTIVE tiles:
+// its cost follows the interfacial region, not the lattice.
+// ---------------------------------------------------------------------------------------------------
+#define TILE_P 1
+#define TILE_M 2
+#define TILE_X 4
+
+__device__ __forceinline__ unsigned tile_class(double phi) {
+    if (fabs(phi - 1.0) <= 1e-7) return TILE_P;
+    if (fabs(phi + 1.0) <= 1e-7) return TILE_M;
+    return TILE_X;  // also NaN
+}
+
+__device__ __forceinline__ void tile_or(unsigned char *arr, int tile, unsigned bits) {
+    unsigned *w = (unsigned *)(arr + (tile & ~3));
+    atomicOr(w, bits << (8 * (tile & 3)));
+}
+
+// one-time: mark[c] = 1 on solid boundary nodes (their phi is derived from fluid neighbours by K3)
+__global__ void k_tile_mark_solid(const Dev P, unsigned char *mark) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.num_solid) mark[P.solid_cell[n]] = 1;
+}
+
+// one-time: class bits of every cell whose phi is read by the gradient stencils but is neither written by the collision
+// kernel (A nodes) nor derived by K3: non-solid ghost cells, solid cells missing from the list.  Tiles that
+// touch the z ghost planes (inlet/outlet values, periodic wrap, halo exchange) are always X.
+__global__ void __launch_bounds__(128) k_tile_static(const Dev P, const unsigned char *mark) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - 2;
+    const int j = (int)blockIdx.y - 2;
+    const int k = (int)blockIdx.z - 2;
+    const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
+    if (i > nx + 3) return;
+    const int c = P.g.cell(i, j, k);
+    const int t = P.g.tile_of(c, P.ntx, P.nty);
+    if (k <= 0 || k >= nz + 1) {
+        tile_or(P.tstat, t, TILE_X);
+        return;
+    }
+    const int a = P.smap[c];
+    if (a >= 0 && a < P.nA) return;  // fluid node: dynamic class
+    if (mark[c]) return;             // K3 node: derived from fluid nodes of the neighbourhood
+    auto inG = [&](int ii, int jj, int kk) {
+        return ii >= -1 && ii <= nx + 2 && jj >= -1 && jj <= ny + 2 && kk >= -1 && kk <= nz + 2 && P.walls[P.g.cell(ii, jj, kk)] != 1;
+    };
+    bool rel = inG(i, j, k);
+#pragma unroll
+    for (int q = 1; q < 19 && !rel; q++) rel = inG(i + EX(q), j + EY(q), k + EZ(q));
+    if (rel) tile_or(P.tstat, t, tile_class(P.phi[c]));
+}
+
+// per step: U = OR of the class bits over the 27-tile neighbourhood; quiet iff U is one single class and equals the
+// previous step's U.  Active tiles are appended to tact; every tile within one tile of an active tile is appended
+// (once, guarded by a per-step stamp) to tk3: K3 must refresh phi on every solid node an active evaluation can read.
+// Also clears the class buffer the next step will write.
+__global__ void k_tile_update(const Dev P, int cur, int stamp) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.ntiles) return;
+    const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
+    unsigned U = 0;
+    for (int dz = -1; dz <= 1; dz++) {
+        const int z = tz + dz;
+        if (z < 0 || z >= P.ntz) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = ty + dy;
+            if (y < 0 || y >= P.nty) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                const int x = tx + dx;
+                if (x < 0 || x >= P.ntx) continue;
+                const int o = x + P.ntx * (y + P.nty * z);
+                U |= (unsigned)P.tcls[cur][o] | (unsigned)P.tstat[o];
+            }
+        }
+    }
+    const unsigned prev = P.tU[cur ^ 1][t];
+    const bool quiet = (U == prev && (U == 0 || U == TILE_P || U == TILE_M));
+    P.tU[cur][t] = (unsigned char)U;
+    P.tquiet[t] = quiet ? 1 : 0;
+    P.tcls[cur ^ 1][t] = 0;
+    if (quiet) return;
+    P.tact[atomicAdd(&P.tcount[0], 1)] = t;
+    for (int dz = -1; dz <= 1; dz++) {
+        const int z = tz + dz;
+        if (z < 0 || z >= P.ntz) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = ty + dy;
+            if (y < 0 || y >= P.nty) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                const int x = tx + dx;
+                if (x < 0 || x >= P.ntx) continue;
+                const int o = x + P.ntx * (y + P.nty * z);
+                if (atomicExch(&P.tk3stamp[o], stamp) != stamp) P.tk3[atomicAdd(&P.tcount[1], 1)] = o;
+            }
+        }
+    }
+}
+
+// every tile active (explicit mflbm_color_gradient)
+__global__ void k_tile_all(const Dev P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.ntiles) return;
+    P.tact[t] = t;
+    P.tk3[t] = t;
+    if (t == 0) {
+        P.tcount[0] = P.ntiles;
+        P.tcount[1] = P.ntiles;
+    }
+}
+
+// tile-driven launch shape: persistent blocks walk a tile list; the threads of a block share the entries of one tile
+template <int K>
+__global__ void __launch_bounds__(64) k_chain_tiles(const Dev P) {
+    const int *__restrict__ list = K == 3 ? P.tk3 : P.tact;
+    const int count = P.tcount[K == 3 ? 1 : 0];
+    const int *__restrict__ start = (K == 3 || K == 6) ? P.ts_start : (K == 4 ? P.tg_start : P.tf_start);
+    for (int t = blockIdx.x; t < count; t += gridDim.x) {
+        const int tile = list[t];
+        const int e1 = start[tile + 1];
+        for (int e = start[tile] + threadIdx.x; e < e1; e += 64) {
+            if (K == 3) phi_solid_at(P, e);
+            else if (K == 4) gradient_at<true>(P, P.gcell[e]);
+            else if (K == 5) alter_at(P, e);
+            else cn_solid_at(P, e);
+        }
+    }
+}
+
+// every tile active: after create / upload / compute_macro_vars / an explicit mflbm_color_gradient
+void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st) {
     const Dev &P = c->d;
+    if (!P.use_tiles) return;
+    const size_t n = (size_t)P.ntiles + 4;
+    cudaMemsetAsync(P.tcls[0], 0, n, st);
+    cudaMemsetAsync(P.tcls[1], 0, n, st);
+    cudaMemsetAsync(P.tU[0], TILE_X, n, st);
+    cudaMemsetAsync(P.tU[1], TILE_X, n, st);
+    cudaMemsetAsync(P.tquiet, 0, n, st);
+}
+
+// (re)computes the static class bits; needs walls, smap, the solid list and phi on the device
+int tiles_prepare(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.use_tiles || c->tiles_static_ready) return 0;
+    unsigned char *mark = nullptr;
+    if (cudaMalloc((void **)&mark, (size_t)P.g.ntot) != cudaSuccess) return -1;
+    cudaMemsetAsync(mark, 0, (size_t)P.g.ntot, st);
+    cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles + 4, st);
+    cudaMemsetAsync(P.tk3stamp, 0, (size_t)P.ntiles * sizeof(int), st);
+    if (P.num_solid > 0) {
+        k_tile_mark_solid<<<(P.num_solid + 255) / 256, 256, 0, st>>>(P, mark);
+        c->launches++;
+    }
+    dim3 grid((P.g.nx + 6 + 127) / 128, P.g.ny + 6, P.g.nz + 6);
+    k_tile_static<<<grid, 128, 0, st>>>(P, mark);
+    c->launches++;
+    cudaStreamSynchronize(st);
+    cudaFree(mark);
+    launch_tiles_reset(c, st);
+    c->tile_stamp = 0;
+    c->tiles_static_ready = true;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// phi on ALL listed solid boundary nodes (download / monitors want the reference's values everywhere)
+void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.multiphase || P.num_solid <= 0) return;
+    k_phi_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
+    c->launches++;
+    c->solid_phi_stale = false;
+}
+
+// stepping = true: called from mflbm_step right after the collision kernel, which recorded the phi classes of this
+// step; otherwise (explicit mflbm_color_gradient, e.g. before the first step) every tile is evaluated.
+void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
+    Dev &P = c->d;
     if (!P.multiphase) return;
+    if (P.use_tiles) {
+        const int nb = (P.ntiles + 127) / 128;
+        if (stepping) {
+            cudaMemsetAsync(P.tcount, 0, 2 * sizeof(int), st);
+            k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp);
+            P.tile_cur ^= 1;
+            c->solid_phi_stale = true;
+        } else {
+            launch_tiles_reset(c, st);
+            k_tile_all<<<nb, 128, 0, st>>>(P);
+            c->solid_phi_stale = false;
+        }
+        const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
+        if (P.num_solid > 0) k_chain_tiles<3><<<grid, 64, 0, st>>>(P);
+        if (P.nG > 0) k_chain_tiles<4><<<grid, 64, 0, st>>>(P);
+        if (P.num_fluid > 0) k_chain_tiles<5><<<grid, 64, 0, st>>>(P);
+        if (P.num_solid > 0) k_chain_tiles<6><<<grid, 64, 0, st>>>(P);
+        c->launches += 1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0);
+        return;
+    }
     if (P.num_solid > 0) {
         k_phi_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
         c->launches++;

@@ -59,7 +59,14 @@ __global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, in
     if (MP) {
         // c_norm == 0 (no interface nearby: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature) lets the sparse
         // layout skip the normal loads and the curvature stencil.  Exact: the skipped terms are +-0.
-        const double c_norm = P.c_norm[c];
+        // Quiet tile (uniform phi around, see kernels_gradient.cu): c_norm is known to be 0 without reading it.
+        int tile = 0;
+        bool quiet = false;
+        if (SPARSE && P.use_tiles) {
+            tile = P.g.tile_of(c, P.ntx, P.nty);
+            quiet = P.tquiet[tile] != 0;
+        }
+        const double c_norm = quiet ? 0.0 : P.c_norm[c];
         double cnx = 0.0, cny = 0.0, cnz = 0.0, curv = 0.0;
         if (!SPARSE) {
             cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c]; curv = P.curv[c];
@@ -69,6 +76,13 @@ __global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, in
         }
         const double phi = collide_mp(P, a, b, cnx, cny, cnz, curv, c_norm);
         P.phi[c] = phi;
+        if (SPARSE && P.use_tiles) {  // record the phi class of this node's tile: one atomic per (warp, tile, class)
+            const unsigned bits = fabs(phi - 1.0) <= 1e-7 ? 1u : (fabs(phi + 1.0) <= 1e-7 ? 2u : 4u);
+            const unsigned key = ((unsigned)tile << 3) | bits;
+            const unsigned peers = __match_any_sync(__activemask(), key);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1)
+                atomicOr((unsigned *)(P.tcls[P.tile_cur] + (tile & ~3)), bits << (8 * (tile & 3)));
+        }
     } else {
         collide_sp(P, a);
     }

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mflbm_internal.cuh"
@@ -145,6 +146,9 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->comm = nullptr;
     ctx->macro_alloc = false;
     ctx->pdf_alloc = false;
+    ctx->tiles_static_ready = false;
+    ctx->solid_phi_stale = false;
+    ctx->tile_stamp = 0;
     ctx->prof = false;
     ctx->prof_used = 0;
     ctx->prof_ms = 0;
@@ -271,6 +275,16 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
 //   S nodes  = every other node of the 0..n+1 box that is a D3Q19 neighbour of an A node
 //   nbr[q-1][n] = active index of x_n + e_q   (always exists by construction)
 // ---------------------------------------------------------------------------------------------------
+// Stable counting sort of list entries by tile: order[new position] = old index, start = CSR ranges [ntiles+1].
+static void sort_by_tile(const std::vector<int> &tile, int ntiles, std::vector<int> &order, std::vector<int> &start) {
+    start.assign((size_t)ntiles + 1, 0);
+    for (int t : tile) start[(size_t)t + 1]++;
+    for (int t = 0; t < ntiles; t++) start[(size_t)t + 1] += start[t];
+    std::vector<int> pos(start.begin(), start.end() - 1);
+    order.resize(tile.size());
+    for (size_t n = 0; n < tile.size(); n++) order[(size_t)pos[tile[n]]++] = (int)n;
+}
+
 static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i fastest */) {
     Dev &d = ctx->d;
     const Grid &g = d.g;
@@ -365,6 +379,17 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
                 if (W(i, j, k) != 1) gcell[n++] = g.cell(i, j, k);
     }
     d.nG = (int)nG;
+    if (d.use_tiles && nG > 0) {  // tile-driven gradient chain: gcell grouped by tile (raster order inside a tile)
+        std::vector<int> tile((size_t)nG), order, start;
+#pragma omp parallel for schedule(static)
+        for (long long n = 0; n < nG; n++) tile[(size_t)n] = g.tile_of(gcell[(size_t)n], d.ntx, d.nty);
+        sort_by_tile(tile, d.ntiles, order, start);
+        std::vector<int> sorted((size_t)nG);
+#pragma omp parallel for schedule(static)
+        for (long long n = 0; n < nG; n++) sorted[(size_t)n] = gcell[(size_t)order[(size_t)n]];
+        gcell.swap(sorted);
+        CU(cudaMemcpy(d.tg_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (dev_alloc(ctx, &d.gcell, gcell.size(), false)) return MFLBM_ERR_CUDA;
     CU(cudaMemcpy(d.gcell, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
     d.nA = nA;
@@ -399,6 +424,21 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     }
     d.sparse = variant == 2;
     d.full_curv = variant == 1;
+    d.use_tiles = (d.sparse && d.multiphase && !getenv("MFLBM_NO_TILES")) ? 1 : 0;
+    if (d.use_tiles) {
+        d.ntx = g.sx / 8;
+        d.nty = (g.ny + 8 + 3) / 4;
+        d.ntz = (g.nz + 8 + 3) / 4;
+        d.ntiles = d.ntx * d.nty * d.ntz;
+        d.tile_cur = 0;
+        const size_t nt = (size_t)d.ntiles + 4;
+        if (dev_alloc(ctx, &d.tcls[0], nt) || dev_alloc(ctx, &d.tcls[1], nt) || dev_alloc(ctx, &d.tstat, nt) ||
+            dev_alloc(ctx, &d.tU[0], nt) || dev_alloc(ctx, &d.tU[1], nt) || dev_alloc(ctx, &d.tquiet, nt) ||
+            dev_alloc(ctx, &d.tg_start, nt) || dev_alloc(ctx, &d.ts_start, nt) || dev_alloc(ctx, &d.tf_start, nt) ||
+            dev_alloc(ctx, &d.tact, nt) || dev_alloc(ctx, &d.tk3, nt) || dev_alloc(ctx, &d.tk3stamp, nt) ||
+            dev_alloc(ctx, &d.tcount, 4))
+            return MFLBM_ERR_CUDA;
+    }
     size_t n = g.ntot;
     if (d.sparse) {
         if (build_active_set(ctx, walls)) return MFLBM_ERR_CUDA;
@@ -496,6 +536,7 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (xfer_pdf(ctx, d.f[q], h->f[q], true)) return MFLBM_ERR_CUDA;
         if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], true)) return MFLBM_ERR_CUDA;
     }
+    if (h->walls || h->phi || h->solid_boundary_nodes) ctx->tiles_static_ready = false;  // quiet-tile state restarts
     if (d.multiphase) {
         if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, true)) return MFLBM_ERR_CUDA;
         if (h->phi_old) {
@@ -507,6 +548,8 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
     }
     if (xfer(ctx, d.f_convec, h->f_convec_bc, 1, 19, -3, true)) return MFLBM_ERR_CUDA;
     if (xfer(ctx, d.w_in, h->w_in, 1, 1, -3, true)) return MFLBM_ERR_CUDA;
+    if (d.multiphase && (h->solid_boundary_nodes || h->fluid_boundary_nodes) && !ctx->pdf_alloc)
+        return fail(ctx, MFLBM_ERR_STATE, "boundary-node lists uploaded before the wall array");
     if (d.multiphase && h->solid_boundary_nodes && d.num_solid > 0) {
         std::vector<int> cell(d.num_solid);
         std::vector<unsigned> mask(d.num_solid);
@@ -529,6 +572,19 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             mask[n] = m;
             law[n] = s.la_weight;
         }
+        if (d.use_tiles) {  // group by tile for the tile-driven chain (entries are independent of each other)
+            std::vector<int> tile(d.num_solid), order, start;
+            for (int n = 0; n < d.num_solid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
+            sort_by_tile(tile, d.ntiles, order, start);
+            std::vector<int> cell2(d.num_solid);
+            std::vector<unsigned> mask2(d.num_solid);
+            std::vector<double> law2(d.num_solid);
+            for (int n = 0; n < d.num_solid; n++) {
+                cell2[n] = cell[order[n]]; mask2[n] = mask[order[n]]; law2[n] = law[order[n]];
+            }
+            cell.swap(cell2); mask.swap(mask2); law.swap(law2);
+            CU(cudaMemcpy(d.ts_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
         CU(cudaMemcpy(d.solid_cell, cell.data(), cell.size() * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.solid_mask, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.solid_law, law.data(), law.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -544,6 +600,19 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             nw[5 * n + 0] = s.nwx; nw[5 * n + 1] = s.nwy; nw[5 * n + 2] = s.nwz;
             nw[5 * n + 3] = cos(s.theta);  // dcos/dsin of MP/Phase_gradient.F90:238-242, evaluated once by the host libm
             nw[5 * n + 4] = sin(s.theta);
+        }
+        if (d.use_tiles) {
+            std::vector<int> tile(d.num_fluid), order, start;
+            for (int n = 0; n < d.num_fluid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
+            sort_by_tile(tile, d.ntiles, order, start);
+            std::vector<int> cell2(d.num_fluid);
+            std::vector<double> nw2((size_t)5 * d.num_fluid);
+            for (int n = 0; n < d.num_fluid; n++) {
+                cell2[n] = cell[order[n]];
+                for (int m = 0; m < 5; m++) nw2[(size_t)5 * n + m] = nw[(size_t)5 * order[n] + m];
+            }
+            cell.swap(cell2); nw.swap(nw2);
+            CU(cudaMemcpy(d.tf_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
         CU(cudaMemcpy(d.fluid_cell, cell.data(), cell.size() * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.fluid_nw, nw.data(), nw.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -562,6 +631,10 @@ extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], false)) return MFLBM_ERR_CUDA;
     }
     if (d.multiphase) {
+        if (h->phi && ctx->solid_phi_stale) {  // K3 was skipped on quiet tiles: give the caller the reference's values
+            launch_phi_solid_refresh(ctx, ctx->s_main);
+            CU(cudaGetLastError());
+        }
         if (d.sparse && h->curv) {  // not maintained per step on the sparse layout: evaluate K7 now (fluid nodes)
             launch_curvature(ctx, ctx->s_main);
             CU(cudaGetLastError());
@@ -695,6 +768,7 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
     const int nz = cfg.nz;
     const bool odd = (ntime % 2) != 0;
     cudaStream_t s = ctx->s_main;
+    if (tiles_prepare(ctx, s)) return fail(ctx, MFLBM_ERR_CUDA, "quiet-tile setup failed");
     if (ctx->comm) {
         // boundary slabs first, exchange on the high-priority halo stream while the interior runs
         // (MP/Main_multiphase.F90:358-387, :423-458)
@@ -711,7 +785,7 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
         if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
     }
     launch_bc(ctx, s, odd);
-    launch_color_gradient(ctx, s);
+    launch_color_gradient(ctx, s, true);
     return check_launch(ctx);
 }
 
@@ -734,7 +808,8 @@ extern "C" int mflbm_run(mflbm_ctx *ctx, int ntime0, int nsteps) {
 extern "C" int mflbm_color_gradient(mflbm_ctx *ctx) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
     CU(cudaSetDevice(ctx->device));
-    launch_color_gradient(ctx, ctx->s_main);
+    if (tiles_prepare(ctx, ctx->s_main)) return fail(ctx, MFLBM_ERR_CUDA, "quiet-tile setup failed");
+    launch_color_gradient(ctx, ctx->s_main, false);
     return check_launch(ctx);
 }
 
@@ -742,7 +817,11 @@ extern "C" int mflbm_compute_macro_vars(mflbm_ctx *ctx) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
     CU(cudaSetDevice(ctx->device));
     if (ensure_macro(ctx)) return MFLBM_ERR_CUDA;
+    // phi on solid nodes of 1..n is zeroed below (MP/Misc.F90:424); the listed solid nodes outside 1..n keep the last
+    // K3 value, so refresh the ones quiet tiles skipped first, and let the next gradient chain evaluate every tile
+    if (ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, ctx->s_main);
     launch_macro(ctx, ctx->s_main);
+    launch_tiles_reset(ctx, ctx->s_main);
     return check_launch(ctx);
 }
 
@@ -812,6 +891,7 @@ extern "C" int mflbm_monitor_steady_phasefield(mflbm_ctx *ctx, double *umax_sq, 
     if (!ctx || !umax_sq || !d_phi_max) return fail(ctx, MFLBM_ERR_ARG, "null argument");
     if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
     if (ensure_phi_old(ctx)) return MFLBM_ERR_CUDA;
+    if (ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, ctx->s_main);
     int rc = mflbm_compute_macro_vars(ctx);
     if (rc) return rc;
     const int nz = ctx->cfg.nz;
@@ -899,6 +979,22 @@ extern "C" int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long 
     *collide_launches = ctx->prof_launches;
     ctx->prof_ms = 0;
     ctx->prof_launches = 0;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nquiet) {
+    if (!ctx || !ntiles || !nquiet) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    *ntiles = 0;
+    *nquiet = 0;
+    if (!ctx->d.use_tiles) return MFLBM_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<unsigned char> h((size_t)ctx->d.ntiles);
+    CU(cudaStreamSynchronize(ctx->s_main));
+    CU(cudaMemcpy(h.data(), ctx->d.tquiet, h.size(), cudaMemcpyDeviceToHost));
+    long long q = 0;
+    for (unsigned char b : h) q += b;
+    *ntiles = ctx->d.ntiles;
+    *nquiet = q;
     return MFLBM_OK;
 }
 

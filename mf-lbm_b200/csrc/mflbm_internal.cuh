@@ -45,6 +45,13 @@ struct Grid {
     __host__ __device__ __forceinline__ int off(int q) const { return EX(q) + sx * EY(q) + sxy * EZ(q); }
     __host__ __device__ __forceinline__ int cell2(int i, int j) const { return base + (i - 1) + sx * (j + 3); }  // 2-D plane fields
     int plane_cells() const { return sxy; }
+    // tile of 8x4x4 cells containing linear cell c (ntx = sx/8 tiles per row, nty tiles per plane column)
+    __host__ __device__ __forceinline__ int tile_of(int c, int ntx, int nty) const {
+        const unsigned r = (unsigned)(c - (base - 4));  // (i+3) + sx*(j+3) + sxy*(k+3)
+        const unsigned kz = r / (unsigned)sxy, r2 = r - kz * (unsigned)sxy;
+        const unsigned jy = r2 / (unsigned)sx, ix = r2 - jy * (unsigned)sx;
+        return (int)((ix >> 3) + (unsigned)ntx * ((jy >> 2) + (unsigned)nty * (kz >> 2)));
+    }
     // first cell of the contiguous storage of plane k (includes the row paddings): cell(-3,-3,k)
     __host__ __device__ __forceinline__ int plane_begin(int k) const { return base - 4 + sxy * (k + 3); }
 };
@@ -80,6 +87,22 @@ struct Dev {
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
     int nG;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
+    // phi-uniformity tiles (sparse multiphase layout, DESIGN.md "Quiet tiles"): the padded grid is cut into tiles of
+    // 8x4x4 cells; the collision kernel records which phi classes occur among the fluid nodes of each tile
+    // (P: |phi-1|<=1e-7, M: |phi+1|<=1e-7, X: anything else).  A tile whose 27-tile neighbourhood shows one single
+    // class for two consecutive steps is QUIET: every colour gradient there is below the reference's 1e-6 cut-off,
+    // i.e. exactly zero, so the gradient chain K3..K6 and the c_norm read of the collision kernel are skipped.
+    int use_tiles;
+    int ntx, nty, ntz, ntiles;
+    int tile_cur;            // which tcls / tU buffer the current step writes
+    unsigned char *tcls[2];  // per-step class bits of the fluid nodes (atomicOr by k_collide)
+    unsigned char *tstat;    // class bits of cells whose phi never changes (ghost / unlisted cells), X on z-ghost tiles
+    unsigned char *tU[2];    // class bits OR-ed over the 27-tile neighbourhood, this step and the previous one
+    unsigned char *tquiet;   // 1: tile is quiet
+    int *tg_start, *ts_start, *tf_start;  // [ntiles+1] CSR ranges of gcell / the solid list / the fluid list (sorted by tile)
+    int *tact, *tk3;         // [ntiles] active tiles (K4,K5,K6) / tiles within one tile of an active tile (K3), per step
+    int *tcount;             // [2] lengths of tact, tk3
+    int *tk3stamp;           // [ntiles] step stamp guarding the tk3 append
     // scalars
     int multiphase, mrt;
     double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
@@ -116,6 +139,9 @@ struct mflbm_ctx {
     bool open_z;
     bool macro_alloc;
     bool pdf_alloc;
+    int tile_stamp;
+    bool tiles_static_ready;  // tstat computed for the current phi / wall / node-list upload
+    bool solid_phi_stale;     // phi on solid boundary nodes of quiet tiles was not refreshed by the last gradient chain
     double *halo_buf[4];  // sparse NCCL exchange: send_lo, send_hi, recv_lo, recv_hi
     std::vector<int> kstartA;
     bool prof;                         // per-launch event timing of the collision kernel
@@ -131,7 +157,10 @@ void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1);
 void launch_fill_smap(mflbm_ctx *c, cudaStream_t st);
 void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev);
 void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack);
-void launch_color_gradient(mflbm_ctx *c, cudaStream_t st);
+void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping = false);
+void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st);
+void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);
+int tiles_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_curvature(mflbm_ctx *c, cudaStream_t st);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);

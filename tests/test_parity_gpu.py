@@ -132,3 +132,27 @@ def test_monitors_match_oracle(layout):
     assert c["i_w"] == co["i_w"] and c["i_nw"] == co["i_nw"]
     assert c["pre_w"] == pytest.approx(co["pre_w"], rel=1e-11) and c["pre_nw"] == pytest.approx(co["pre_nw"], rel=1e-11)
     ctx.close()
+
+
+@pytest.mark.parametrize("ca", [1e-4, 5e-3])
+def test_quiet_tiles_long_run_bit_exact(ca):
+    """Sparse layout, strict build, long run: the quiet-tile skipping of the colour-gradient chain (DESIGN.md "Quiet
+    tiles") must stay bit-exact while the interface moves through tiles that were quiet, across monitor calls
+    (compute_macro_vars zeroes phi at walls) and across downloads (which refresh the skipped solid-node phi)."""
+    o = make_oracle(modify_geometry_cmd=1, ca_0=ca)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=2)
+    o.color_gradient(); ctx.color_gradient()
+    t = 1
+    seen_quiet = 0
+    for nsteps, mon in ((50, False), (150, True), (200, False), (200, True)):
+        _run_both(o, ctx, nsteps, t)
+        t += nsteps
+        nt, nq = ctx.tile_stats()
+        seen_quiet = max(seen_quiet, nq)
+        assert nt > 0
+        if mon:
+            m, mo = ctx.monitor(), o.monitor()
+            assert m["umax"] == pytest.approx(mo["umax"], rel=1e-11)
+        compare_state(ctx, o, 0.0, sparse=True)
+    assert seen_quiet > 0, "the run never had a quiet tile: the skipping path was not exercised"
+    ctx.close()

@@ -18,11 +18,25 @@
 namespace mflbm {
 
 template <bool MP, bool ODD, bool SPARSE>
-__global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, int n1) {
+__global__ void __launch_bounds__(128, MP ? 3 : 4) k_collide(const Dev P, int k0, int n0, int n1) {
     int c, n = 0;
+    __shared__ uint4 s_adj[SPARSE && ODD ? 4 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
     if (SPARSE) {
-        n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-        if (n >= n1) return;
+        // n0 is rounded down to a multiple of 32 by the launcher so that lane == n & 31 (the adjacency is per warp of
+        // 32 consecutive A nodes)
+        n = (n0 & ~31) + blockIdx.x * blockDim.x + threadIdx.x;
+        if (ODD) {
+            // stage this warp's 37 adjacency records (592 contiguous bytes) in shared memory with one coalesced load
+            // wave; decoding them straight from global memory makes ptxas chain 18 load->use round trips (measured)
+            const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+            if ((n & ~31) < n1) {
+                const uint4 *__restrict__ rec = P.adj + (size_t)(n >> 5) * MFLBM_ADJ_REC;
+                s_adj[wib][lane] = __ldg(rec + lane);
+                if (lane < MFLBM_ADJ_REC - 32) s_adj[wib][32 + lane] = __ldg(rec + 32 + lane);
+            }
+            __syncwarp();
+        }
+        if (n < n0 || n >= n1) return;
         c = P.cellA[n];
     } else {
         const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -38,8 +52,17 @@ __global__ void __launch_bounds__(128) k_collide(const Dev P, int k0, int n0, in
     if (ODD) {   // pull f_q from x - e_q (MP/Kernel_multiphase.F90:46-84)
         if (SPARSE) {
             nb[0] = n;
+            const uint4 *rec = s_adj[threadIdx.x >> 5];
+            const int lane = n & 31;
 #pragma unroll
-            for (int q = 1; q < 19; q++) nb[q] = __ldg(P.nbr + (q - 1) * P.nbr_stride + n);
+            for (int q = 1; q < 19; q++) nb[q] = adj_index(rec[1 + 2 * (q - 1)], rec[2 + 2 * (q - 1)], lane, P.nAct);
+            const unsigned irr = rec[0].x;
+            if (irr) {  // warp-uniform and rare: directions with more than five index runs read their indices verbatim
+                const int *__restrict__ row = P.adjfull + (size_t)rec[0].y * 32 + lane;
+#pragma unroll
+                for (int q = 1; q < 19; q++)
+                    if ((irr >> (q - 1)) & 1u) nb[q] = __ldg(row + 32 * __popc(irr & ((1u << (q - 1)) - 1u)));
+            }
         }
 #pragma unroll
         for (int q = 0; q < 19; q++) {
@@ -116,7 +139,7 @@ static void launch_collide_t(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, in
         n0 = c->kstartA[k0];
         n1 = c->kstartA[k1 + 1];
         if (n1 <= n0) return;
-        grid = dim3((n1 - n0 + 127) / 128);
+        grid = dim3((n1 - (n0 & ~31) + 127) / 128);
     } else {
         grid = dim3((P.g.nx + 127) / 128, P.g.ny, k1 - k0 + 1);
     }
@@ -215,26 +238,37 @@ void launch_fill_smap(mflbm_ctx *c, cudaStream_t st) {
 }
 
 // caller's (0:nx+1,0:ny+1,0:nz+1) array <-> active-node list
-__global__ void k_repack_sparse(const Dev P, double *pdf, double *packed, int to_dev) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= P.nAct) return;
-    int c = P.cellA[n] - P.g.base;  // (i-1) + sx*(j+3) + sxy*(k+3)
-    const int k = c / P.g.sxy - 3;
-    c -= (k + 3) * P.g.sxy;
-    int j = c / P.g.sx - 3;
-    int i = c - (j + 3) * P.g.sx + 1;
-    if (i > P.g.nx + 4) {  // low-x ghosts live in the tail padding of the previous row
-        i -= P.g.sx;
-        j += 1;
-    }
-    const size_t p = (size_t)i + (size_t)(P.g.nx + 2) * ((size_t)j + (size_t)(P.g.ny + 2) * k);
-    if (to_dev) pdf[n] = packed[p];
-    else packed[p] = pdf[n];
+// position of dense cell c in the caller's (0:nx+1,0:ny+1,0:nz+1) array
+__device__ __forceinline__ size_t host_pos(const Dev &P, int c) {
+    const unsigned r = (unsigned)(c - (P.g.base - 4));  // (i+3) + sx*(j+3) + sxy*(k+3)
+    const unsigned kz = r / (unsigned)P.g.sxy, r2 = r - kz * (unsigned)P.g.sxy;
+    const unsigned jy = r2 / (unsigned)P.g.sx, ix = r2 - jy * (unsigned)P.g.sx;
+    return (size_t)(ix - 3) + (size_t)(P.g.nx + 2) * ((size_t)(jy - 3) + (size_t)(P.g.ny + 2) * (size_t)(kz - 3));
 }
 
-void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev) {
+// Population array q.  Node entries: n < nAct <-> cell cellA[n].  Link entries: the slot of A node n in direction
+// d = opc(q) holds what the reference keeps in array q at the (non-fluid) cell x_n + e_d.
+__global__ void k_repack_sparse(const Dev P, double *pdf, double *packed, int to_dev, int q) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.nAct) return;
+    const int c = P.cellA[n];
+    const size_t p = host_pos(P, c);
+    if (to_dev) pdf[n] = packed[p];
+    else packed[p] = pdf[n];
+    if (q == 0 || n >= P.nA) return;
+    const int d = OPC(q);
+    const uint4 *__restrict__ rec = P.adj + (size_t)(n >> 5) * MFLBM_ADJ_REC;
+    const int lane = n & 31;
+    if (!((rec[1 + 2 * (d - 1)].x >> lane) & 1u)) return;
+    const int slot = adj_lookup(rec, P.adjfull, d, lane, P.nAct);
+    const size_t pl = host_pos(P, c + P.g.off(d));
+    if (to_dev) pdf[slot] = packed[pl];
+    else packed[pl] = pdf[slot];
+}
+
+void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev, int q) {
     const Dev &P = c->d;
-    k_repack_sparse<<<(P.nAct + 255) / 256, 256, 0, st>>>(P, pdf, packed, to_dev ? 1 : 0);
+    k_repack_sparse<<<(P.nAct + 255) / 256, 256, 0, st>>>(P, pdf, packed, to_dev ? 1 : 0, q);
     c->launches++;
 }
 

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "mflbm_internal.cuh"
 
 using namespace mflbm;
@@ -285,9 +287,17 @@ static void sort_by_tile(const std::vector<int> &tile, int ntiles, std::vector<i
     for (size_t n = 0; n < tile.size(); n++) order[(size_t)pos[tile[n]]++] = (int)n;
 }
 
-static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i fastest */) {
-    Dev &d = ctx->d;
-    const Grid &g = d.g;
+// Host-only part (integer work, OpenMP): node numbering and the compressed adjacency of the odd step.
+struct HostActive {
+    int nA = 0;
+    long long nAct = 0;
+    int nlink[19] = {0};
+    std::vector<int> kstartA, cellA, adjfull;
+    std::vector<uint4> adj;
+};
+
+static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i fastest */, HostActive &H, std::string &err,
+                             bool check) {
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const long long bx = nx + 2, by = ny + 2, bz = nz + 2;  // 0..n+1 box
     auto W = [&](int i, int j, int k) -> int8_t {
@@ -304,13 +314,13 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
             for (int i = 1; i <= nx; i++) c += (W(i, j, k) == 0);
         cntA[k] = c;
     }
-    ctx->kstartA.assign(nz + 3, 0);
-    for (int k = 1; k <= nz + 1; k++) ctx->kstartA[k] = ctx->kstartA[k - 1] + cntA[k - 1];
-    ctx->kstartA[nz + 2] = ctx->kstartA[nz + 1];
-    const int nA = ctx->kstartA[nz + 1];
+    H.kstartA.assign(nz + 3, 0);
+    for (int k = 1; k <= nz + 1; k++) H.kstartA[k] = H.kstartA[k - 1] + cntA[k - 1];
+    H.kstartA[nz + 2] = H.kstartA[nz + 1];
+    const int nA = H.kstartA[nz + 1];
 #pragma omp parallel for schedule(static)
     for (int k = 1; k <= nz; k++) {
-        int n = ctx->kstartA[k];
+        int n = H.kstartA[k];
         for (int j = 1; j <= ny; j++)
             for (int i = 1; i <= nx; i++)
                 if (W(i, j, k) == 0) idx[B(i, j, k)] = n++;
@@ -323,6 +333,7 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
         for (int j = 0; j <= ny + 1; j++)
             for (int i = 0; i <= nx + 1; i++) {
                 if (isA(i, j, k)) continue;
+                if (k > 2 && k < nz - 1) continue;  // outside the cell-addressable zone: served by compact link slots
                 bool s = false;
                 for (int q = 1; q < 19 && !s; q++) s = isA(i + EX(q), j + EY(q), k + EZ(q));
                 if (s) {
@@ -336,7 +347,7 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
     startS[0] = nA;
     for (int k = 1; k <= nz + 2; k++) startS[k] = startS[k - 1] + cntS[k - 1];
     const long long nAct = startS[nz + 2];
-    if (nAct >= (1LL << 31) - 64) return fail(ctx, MFLBM_ERR_ARG, "too many active nodes");
+    if (nAct >= (1LL << 31) - 64) { err = "too many active nodes"; return -1; }
 #pragma omp parallel for schedule(static)
     for (int k = 0; k <= nz + 1; k++) {
         int n = (int)startS[k];
@@ -344,20 +355,148 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
             for (int i = 0; i <= nx + 1; i++)
                 if (idx[B(i, j, k)] == -2) idx[B(i, j, k)] = n++;
     }
-    // cell list and neighbour table
-    std::vector<int> cellA((size_t)nAct);
-    const int stride = (nA + 31) / 32 * 32;
-    std::vector<int> nbr((size_t)18 * (stride > 0 ? stride : 32), 0);
+    // cell list
+    std::vector<int> &cellA = H.cellA;
+    cellA.assign((size_t)nAct, 0);
 #pragma omp parallel for schedule(static)
     for (int k = 0; k <= nz + 1; k++)
         for (int j = 0; j <= ny + 1; j++)
             for (int i = 0; i <= nx + 1; i++) {
                 const int n = idx[B(i, j, k)];
-                if (n < 0) continue;
-                cellA[n] = g.cell(i, j, k);
-                if (n < nA)
-                    for (int q = 1; q < 19; q++) nbr[(size_t)(q - 1) * stride + n] = idx[B(i + EX(q), j + EY(q), k + EZ(q))];
+                if (n >= 0) cellA[n] = g.cell(i, j, k);
             }
+    // Compressed adjacency of the odd step (mflbm_internal.cuh "Adjacency").  For warp w = 32 consecutive A nodes and
+    // direction d the neighbour x+e_d of lane l is either
+    //   a compact LINK slot (x+e_d is neither an A node nor a zone S node: bounce-back storage private to this link),
+    //       index nAct + lbase + rank of the lane among the warp's link lanes, or
+    //   a node index that continues the previous non-link lane's index by +1, or starts a new run (a JUMP, value stored;
+    //       the first four jumps of a record inline, further ones in the overflow array jval).
+    const int nW = (nA + 31) / 32;
+    auto nbr_of = [&](int n, int q) -> int {  // active index of x_n + e_q, or -1 (-> link)
+        const unsigned r = (unsigned)(cellA[n] - (g.base - 4));
+        const unsigned kz = r / (unsigned)g.sxy, r2 = r - kz * (unsigned)g.sxy;
+        const unsigned jy = r2 / (unsigned)g.sx, ix = r2 - jy * (unsigned)g.sx;
+        return idx[B((int)ix - 3 + EX(q), (int)jy - 3 + EY(q), (int)kz - 3 + EZ(q))];
+    };
+    std::vector<int> lcnt((size_t)nW * 18 + 18, 0);
+    std::vector<long long> irr((size_t)nW + 1, 0);  // irregular rows per warp -> exclusive prefix
+    std::vector<unsigned> irrmask((size_t)nW + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < nW; w++) {
+        unsigned im = 0;
+        const int l1 = std::min(32, nA - 32 * w);
+        for (int q = 1; q < 19; q++) {
+            int links = 0, jumps = 0, prev = -2;
+            for (int l = 0; l < l1; l++) {
+                const int v = nbr_of(32 * w + l, q);
+                if (v < 0) { links++; continue; }
+                if (v != prev + 1) jumps++;
+                prev = v;
+            }
+            lcnt[(size_t)w * 18 + (q - 1)] = links;
+            if (jumps > 5) im |= 1u << (q - 1);
+        }
+        irrmask[w] = im;
+        irr[w] = __builtin_popcount(im);
+    }
+    // exclusive prefix sums over the warps
+    long long lsum[18] = {0};
+    for (int w = 0; w < nW; w++)
+        for (int q = 0; q < 18; q++) {
+            const int c = lcnt[(size_t)w * 18 + q];
+            lcnt[(size_t)w * 18 + q] = (int)lsum[q];
+            lsum[q] += c;
+        }
+    long long osum = 0;
+    for (int w = 0; w < nW; w++) {
+        const long long c = irr[w];
+        irr[w] = osum;
+        osum += c;
+    }
+    H.nlink[0] = 0;
+    for (int q = 1; q < 19; q++) {
+        if (nAct + lsum[q - 1] >= (1LL << 31) - 64) { err = "too many active nodes"; return -1; }
+        H.nlink[q] = (int)lsum[q - 1];
+    }
+    if (osum * 32 >= (1LL << 31)) { err = "adjacency: too many irregular rows"; return -1; }
+    std::vector<uint4> &adj = H.adj;
+    std::vector<int> &full = H.adjfull;
+    adj.assign((size_t)std::max(nW, 1) * MFLBM_ADJ_REC, uint4{0, 0, 0, 0});
+    full.assign((size_t)std::max<long long>(osum, 1) * 32, 0);
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < nW; w++) {
+        long long row = irr[w];
+        const int l1 = std::min(32, nA - 32 * w);
+        uint4 *rec = &adj[(size_t)w * MFLBM_ADJ_REC];
+        rec[0] = uint4{irrmask[w], (unsigned)irr[w], 0u, 0u};
+        for (int q = 1; q < 19; q++) {
+            const int lb = lcnt[(size_t)w * 18 + (q - 1)];
+            unsigned smask = 0, jmask = 0;
+            int inl[5] = {0, 0, 0, 0, 0};
+            int jumps = 0, prev = -2, links = 0;
+            const bool irregular = (irrmask[w] >> (q - 1)) & 1u;
+            for (int l = 0; l < l1; l++) {
+                const int v = nbr_of(32 * w + l, q);
+                if (v < 0) {
+                    if (irregular) full[(size_t)row * 32 + l] = (int)nAct + lb + links;
+                    smask |= 1u << l;
+                    links++;
+                    continue;
+                }
+                if (irregular) full[(size_t)row * 32 + l] = v;
+                if (v != prev + 1) {
+                    jmask |= 1u << l;
+                    if (jumps < 5) inl[jumps] = v;
+                    jumps++;
+                }
+                prev = v;
+            }
+            if (irregular) row++;
+            rec[1 + 2 * (q - 1)] = uint4{smask, jmask, (unsigned)lb, (unsigned)inl[0]};
+            rec[2 + 2 * (q - 1)] = uint4{(unsigned)inl[1], (unsigned)inl[2], (unsigned)inl[3], (unsigned)inl[4]};
+        }
+    }
+    H.nA = nA;
+    H.nAct = nAct;
+    if (check) {  // decode every (node, direction) with the device function and compare with the direct lookup
+        long long bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+        for (int n = 0; n < nA; n++) {
+            const int w = n >> 5, l = n & 31;
+            for (int q = 1; q < 19; q++) {
+                const int got = adj_lookup(&adj[(size_t)w * MFLBM_ADJ_REC], full.data(), q, l, (int)nAct);
+                const int v = nbr_of(n, q);
+                if (v >= 0) bad += (got != v);
+                else bad += (got < nAct || got >= nAct + H.nlink[q]);  // a link slot of direction q
+            }
+        }
+        if (bad) { err = "compressed adjacency self-check failed"; return -1; }
+    }
+    return 0;
+}
+
+static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i fastest */) {
+    Dev &d = ctx->d;
+    const Grid &g = d.g;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    auto W = [&](int i, int j, int k) -> int8_t {
+        return walls[(size_t)(i + 1) + (size_t)(nx + 4) * ((size_t)(j + 1) + (size_t)(ny + 4) * (size_t)(k + 1))];
+    };
+    HostActive H;
+    {
+        std::string err;
+        const char *e = getenv("MFLBM_CHECK_ADJ");
+        const bool check = e ? atoi(e) != 0 : ((long long)nx * ny * nz <= 8000000LL);
+        if (build_active_host(g, walls, H, err, check)) return fail(ctx, MFLBM_ERR_ARG, err);
+    }
+    ctx->kstartA = H.kstartA;
+    for (int q = 0; q < 19; q++) d.nlink[q] = H.nlink[q];
+    const int nA = H.nA;
+    const long long nAct = H.nAct;
+    std::vector<int> &cellA = H.cellA;
+    std::vector<uint4> &adj = H.adj;
+    std::vector<int> &full = H.adjfull;
+    ctx->adj_bytes = (long long)(adj.size() * sizeof(uint4) + full.size() * sizeof(int));
     // G list: non-solid cells of the (-1:n+2)^3 box, raster order (where K4 evaluates the colour gradient)
     std::vector<int> gcnt(nz + 5, 0);
 #pragma omp parallel for schedule(static)
@@ -394,12 +533,12 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
     CU(cudaMemcpy(d.gcell, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
     d.nA = nA;
     d.nAct = (int)nAct;
-    d.nbr_stride = stride > 0 ? stride : 32;
-    if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.nbr, nbr.size(), false) ||
-        dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))
+    if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.adj, adj.size(), false) ||
+        dev_alloc(ctx, &d.adjfull, full.size(), false) || dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))
         return MFLBM_ERR_CUDA;
     CU(cudaMemcpy(d.cellA, cellA.data(), (size_t)nAct * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.nbr, nbr.data(), nbr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.adj, adj.data(), adj.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.adjfull, full.data(), full.size() * sizeof(int), cudaMemcpyHostToDevice));
     launch_fill_smap(ctx, ctx->s_main);
     CU(cudaStreamSynchronize(ctx->s_main));
     return 0;
@@ -445,8 +584,10 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
         n = (size_t)d.nAct + 64;
     }
     for (int q = 0; q < 19; q++) {
-        if (dev_alloc(ctx, &d.f[q], n)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && dev_alloc(ctx, &d.gg[q], n)) return MFLBM_ERR_CUDA;
+        // sparse: array q also holds the compact link slots of direction opc(q) behind the node entries
+        const size_t nq = d.sparse ? n + (size_t)d.nlink[OPC(q)] : n;
+        if (dev_alloc(ctx, &d.f[q], nq)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && dev_alloc(ctx, &d.gg[q], nq)) return MFLBM_ERR_CUDA;
     }
     ctx->pdf_alloc = true;
     return 0;
@@ -502,7 +643,7 @@ static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, i
 // one population array: caller's (0:nx+1,0:ny+1,0:nz+1) array <-> device (dense grid or active-node list).
 // Sparse download overwrites only the active entries of the caller's array: all other entries are never
 // touched by the reference either (they keep the values the caller's array already has).
-static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up) {
+static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up, int q) {
     if (!host) return 0;
     if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "populations uploaded before the wall array");
     const Grid &g = ctx->d.g;
@@ -510,7 +651,7 @@ static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up) {
     const size_t n = (size_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
     if (ensure_stage(ctx, n * sizeof(double))) return MFLBM_ERR_CUDA;
     CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
-    launch_repack_sparse(ctx, ctx->s_main, dev, ctx->stage, up);
+    launch_repack_sparse(ctx, ctx->s_main, dev, ctx->stage, up, q);
     if (!up) CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
     CU(cudaStreamSynchronize(ctx->s_main));
     return 0;
@@ -533,8 +674,8 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (setup_populations(ctx, h->walls)) return MFLBM_ERR_CUDA;
     }
     for (int q = 0; q < 19; q++) {
-        if (xfer_pdf(ctx, d.f[q], h->f[q], true)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], true)) return MFLBM_ERR_CUDA;
+        if (xfer_pdf(ctx, d.f[q], h->f[q], true, q)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], true, q)) return MFLBM_ERR_CUDA;
     }
     if (h->walls || h->phi || h->solid_boundary_nodes) ctx->tiles_static_ready = false;  // quiet-tile state restarts
     if (d.multiphase) {
@@ -627,8 +768,8 @@ extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
     const int nz = d.g.nz;
     CU(cudaStreamSynchronize(ctx->s_main));
     for (int q = 0; q < 19; q++) {
-        if (xfer_pdf(ctx, d.f[q], h->f[q], false)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], false)) return MFLBM_ERR_CUDA;
+        if (xfer_pdf(ctx, d.f[q], h->f[q], false, q)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], false, q)) return MFLBM_ERR_CUDA;
     }
     if (d.multiphase) {
         if (h->phi && ctx->solid_phi_stale) {  // K3 was skipped on quiet tiles: give the caller the reference's values
@@ -1000,3 +1141,42 @@ extern "C" int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nq
 
 extern "C" long long mflbm_launch_count(const mflbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" long long mflbm_device_bytes(const mflbm_ctx *ctx) { return ctx ? ctx->bytes : 0; }
+
+// Internal (not part of include/mflbm.h): host-only self-test of the node numbering + compressed adjacency, callable
+// without a GPU (tests/test_adjacency.py).  Returns 0 when every (node, direction) decodes to the direct lookup and the
+// link slots of each direction are a permutation-free ranking; fills counts[0..3] = nA, nAct, total links, irregular rows.
+extern "C" int mflbmx_adjacency_selftest(int nx, int ny, int nz, const int8_t *walls, long long *counts) {
+    Grid g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.sx = (nx + 8 + 15) / 16 * 16;
+    g.sxy = g.sx * (ny + 8);
+    g.base = 16;
+    g.ntot = 16 + g.sxy * (nz + 8) + 16;
+    HostActive H;
+    std::string err;
+    if (build_active_host(g, walls, H, err, true)) {
+        g_err = err;
+        return MFLBM_ERR_STATE;
+    }
+    // link slots: every link lane of direction q must get a distinct slot in [nAct, nAct + nlink[q])
+    for (int q = 1; q < 19; q++) {
+        std::vector<char> seen((size_t)H.nlink[q] + 1, 0);
+        for (int n = 0; n < H.nA; n++) {
+            const int w = n >> 5, l = n & 31;
+            const uint4 *rec = &H.adj[(size_t)w * MFLBM_ADJ_REC];
+            if (!((rec[1 + 2 * (q - 1)].x >> l) & 1u)) continue;
+            const long long slot = (long long)adj_lookup(rec, H.adjfull.data(), q, l, (int)H.nAct) - H.nAct;
+            if (slot < 0 || slot >= H.nlink[q] || seen[(size_t)slot]) {
+                g_err = "link slot collision";
+                return MFLBM_ERR_STATE;
+            }
+            seen[(size_t)slot] = 1;
+        }
+    }
+    if (counts) {
+        long long links = 0;
+        for (int q = 1; q < 19; q++) links += H.nlink[q];
+        counts[0] = H.nA; counts[1] = H.nAct; counts[2] = links; counts[3] = (long long)H.adjfull.size() / 32;
+    }
+    return MFLBM_OK;
+}

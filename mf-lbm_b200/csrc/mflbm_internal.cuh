@@ -79,10 +79,20 @@ struct Dev {
     // storage-only nodes (S: solid-boundary / ghost-plane nodes that are a D3Q19 neighbour of an A node).
     // Scalar fields (phi, cn_*, c_norm, curv, walls, u,v,w,rho) stay on the dense padded grid.
     int sparse;       // 0: PDFs on the dense grid, 1: PDFs on the active-node list
-    int nA, nAct;     // number of A nodes / of all active nodes
-    int nbr_stride;   // row stride of nbr (>= nA, multiple of 32)
-    int *cellA;       // [nAct] dense cell of each active node
-    int *nbr;         // [18][nbr_stride] active index of x+e_q for q=1..18 (row q-1), A nodes only
+    int nA, nAct;     // number of A nodes / of all nodes with an index (A + zone S nodes)
+    int *cellA;       // [nAct] dense cell of each node
+    // Adjacency of the odd step, compressed per warp (32 consecutive A nodes): 37 uint4 per warp,
+    //   [0]        header {irrmask, fullbase, 0, 0}
+    //   [1+2(d-1)] r0 = {smask, jmask, lbase, j0}   for direction d = 1..18
+    //   [2+2(d-1)] r1 = {j1, j2, j3, j4}
+    // smask: lanes whose neighbour x+e_d has no node index -> compact link slot nAct + lbase + popc(smask below lane)
+    // jmask: non-link lanes that start a new index run (run start values j0..j4); the other non-link lanes continue the
+    //        previous non-link lane by +1.
+    // A direction with more than five runs in the warp is IRREGULAR (bit d-1 of irrmask): its 32 indices are stored
+    // verbatim in adjfull, row fullbase + popc(irrmask below d).  72 B/node of int32 indices become ~18.5 B/node.
+    uint4 *adj;       // [ceil(nA/32)][37]
+    int *adjfull;     // [rows][32]
+    int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
     int nG;
@@ -110,6 +120,39 @@ struct Dev {
     double rk_weight2;  // 1/sqrt(2)/36 evaluated on the host like MP/Module.F90:225
 };
 
+#define MFLBM_ADJ_REC 37  // uint4 records per warp
+
+// index of the neighbour of this lane's node in the (regular) direction the records r0,r1 describe (see Dev::adj).
+// Pure ALU on purpose: any load in here would be chained 18 times behind the previous direction's latency.
+__host__ __device__ __forceinline__ int adj_index(const uint4 r0, const uint4 r1, int lane, int nAct) {
+#ifdef __CUDA_ARCH__
+#define MFLBM_POPC(x) __popc(x)
+#define MFLBM_CLZ(x) __clz(x)
+#else
+#define MFLBM_POPC(x) __builtin_popcount(x)
+#define MFLBM_CLZ(x) __builtin_clz(x)
+#endif
+    const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= lane
+    const bool link = (r0.x >> lane) & 1u;
+    const int linkidx = nAct + (int)r0.z + MFLBM_POPC(r0.x & (le >> 1));
+    unsigned p = r0.y & le;  // run starts at or below this lane (empty only for link lanes)
+    p = p ? p : 1u;
+    const int j = MFLBM_POPC(p) - 1;
+    const int last = 31 - MFLBM_CLZ(p);
+    const unsigned between = le & ~(0xffffffffu >> (31 - last));  // lanes last+1 .. lane
+    const int step = MFLBM_POPC(~r0.x & between);
+    const int base = j == 0 ? (int)r0.w : j == 1 ? (int)r1.x : j == 2 ? (int)r1.y : j == 3 ? (int)r1.z : (int)r1.w;
+    return link ? linkidx : base + step;
+}
+
+// host-side / slow-path lookup including the irregular rows (the collision kernel has its own batched version)
+__host__ __device__ __forceinline__ int adj_lookup(const uint4 *rec /* this warp's 37 records */, const int *adjfull, int q,
+                                                   int lane, int nAct) {
+    const uint4 hdr = rec[0];
+    if ((hdr.x >> (q - 1)) & 1u) return adjfull[((size_t)hdr.y + MFLBM_POPC(hdr.x & ((1u << (q - 1)) - 1u))) * 32 + lane];
+    return adj_index(rec[1 + 2 * (q - 1)], rec[2 + 2 * (q - 1)], lane, nAct);
+}
+
 }  // namespace mflbm
 
 struct ncclComm;
@@ -123,6 +166,7 @@ struct mflbm_ctx {
     cudaEvent_t ev_t0, ev_t1, ev_slab, ev_halo, ev_fork;
     std::vector<void *> allocs;
     long long bytes;
+    long long adj_bytes;  // size of the compressed adjacency
     long long launches;
     std::string err;
     // reduction scratch
@@ -155,7 +199,7 @@ namespace mflbm {
 // launchers implemented in the .cu files
 void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1);
 void launch_fill_smap(mflbm_ctx *c, cudaStream_t st);
-void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev);
+void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev, int q);
 void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack);
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping = false);
 void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st);

@@ -1,0 +1,58 @@
+"""CPU test of the integer machinery of the sparse population layout: node numbering, compact link slots and the
+per-warp compressed adjacency of the odd step (mf-lbm_b200/csrc/mflbm_internal.cuh "Adjacency").  The library's host-only
+self-test decodes every (node, direction) with the very function the CUDA kernel uses and compares it with the direct
+neighbour lookup; integer work must be bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mflbm_b200 as M
+from helpers import make_oracle
+
+
+def _selftest(walls):
+    M.build()
+    lib = M.load()
+    fn = lib.mflbmx_adjacency_selftest
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong * 4)]
+    w = np.asfortranarray(walls, dtype=np.int8)
+    nx, ny, nz = (s - 4 for s in w.shape)
+    counts = (C.c_longlong * 4)()
+    rc = fn(nx, ny, nz, w.ctypes.data, C.byref(counts))
+    assert rc == 0, lib.mflbm_last_error(None).decode()
+    return list(counts)
+
+
+def _with_ghosts(core, wall_xy=True):
+    """(nx,ny,nz) 0/1 array -> walls(-1:n+2)^3 with solid x/y ghost layers like a walled channel and open z ghosts"""
+    nx, ny, nz = core.shape
+    w = np.ones((nx + 4, ny + 4, nz + 4), np.int8) if wall_xy else np.zeros((nx + 4, ny + 4, nz + 4), np.int8)
+    w[2:-2, 2:-2, :] = 0
+    w[2:-2, 2:-2, 2:-2] = core
+    return w
+
+
+def test_c1_tube_sphere_adjacency():
+    o = make_oracle(modify_geometry_cmd=1)
+    nA, nAct, links, ovf = _selftest(o.walls)
+    assert nA == 73936                      # pore_sum of C1
+    assert nAct >= nA and links > 0
+
+
+@pytest.mark.parametrize("shape,p,seed", [((33, 17, 40), 0.3, 1), ((64, 8, 9), 0.6, 2), ((7, 5, 4), 0.5, 3), ((40, 40, 12), 0.05, 4),
+                                          ((31, 31, 31), 0.9, 5)])
+def test_random_media_adjacency(shape, p, seed):
+    rng = np.random.default_rng(seed)
+    core = (rng.random(shape) < p).astype(np.int8)
+    for wall_xy in (True, False):
+        nA, nAct, links, ovf = _selftest(_with_ghosts(core, wall_xy))
+        interior = core if wall_xy else core
+        assert nA == int((interior == 0).sum())
+
+
+def test_all_fluid_and_all_solid():
+    nA, nAct, links, ovf = _selftest(_with_ghosts(np.zeros((20, 12, 10), np.int8)))
+    assert nA == 20 * 12 * 10
+    nA, nAct, links, ovf = _selftest(_with_ghosts(np.ones((6, 6, 6), np.int8)))
+    assert nA == 0 and links == 0

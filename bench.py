@@ -42,8 +42,9 @@ def workload_spec(name, n_gpus):
     """Control-file overrides + geometry recipe for each BASELINE.json config."""
     if name == "c3":  # configs[2] (N=1) / weak-scaling stack (N>1), SURVEY 8(d) C3/C5 physics
         n = int(os.environ.get("MFLBM_BENCH_N", "512"))
+        por = float(os.environ.get("MFLBM_BENCH_POROSITY", "0.36"))  # developer knob; the BASELINE config is 0.36
         return dict(multiphase=True, nx=n, ny=n, nz=n * n_gpus, periodic=False,
-                    geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=1, buffer=10),
+                    geometry=dict(porosity=por, rmin=8.0, rmax=20.0, seed=1, buffer=10),
                     control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
                                  RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
                                  initial_interface_position=8.0, initial_fluid_distribution_option=1,

@@ -17,8 +17,10 @@
 
 namespace mflbm {
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool MP, bool ODD, bool SPARSE>
-__global__ void __launch_bounds__(128, MP ? 3 : 4) k_collide(const Dev P, int k0, int n0, int n1) {
+__global__ void __launch_bounds__(128, 4) k_collide(const Dev P, int k0, int n0, int n1) {
     int c, n = 0;
     __shared__ uint4 s_adj[SPARSE && ODD ? 4 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
     if (SPARSE) {
@@ -52,23 +54,68 @@ __global__ void __launch_bounds__(128, MP ? 3 : 4) k_collide(const Dev P, int k0
     if (ODD) {   // pull f_q from x - e_q (MP/Kernel_multiphase.F90:46-84)
         if (SPARSE) {
             nb[0] = n;
+            a[0] = P.f[0][n];
+            if (MP) b[0] = P.gg[0][n];
             const uint4 *rec = s_adj[threadIdx.x >> 5];
+            const int *reci = reinterpret_cast<const int *>(rec);
             const int lane = n & 31;
-#pragma unroll
-            for (int q = 1; q < 19; q++) nb[q] = adj_index(rec[1 + 2 * (q - 1)], rec[2 + 2 * (q - 1)], lane, P.nAct);
+            const unsigned le = 0xffffffffu >> (31 - lane), lt = le >> 1;
             const unsigned irr = rec[0].x;
-            if (irr) {  // warp-uniform and rare: directions with more than five index runs read their indices verbatim
+            if (irr == 0) {
+                // decode direction d and issue its population loads right away, so that the memory system is busy while
+                // the remaining directions are decoded (pure LDS + ALU, ~16 instructions each)
+#pragma unroll
+                for (int d = 1; d < 19; d++) {
+                    const uint4 r0 = rec[1 + 2 * (d - 1)];
+                    unsigned p = r0.y & le;
+                    p = p ? p : 1u;
+                    const int last = 31 - __clz(p);
+                    const int base = reci[4 * (1 + 2 * (d - 1)) + 2 + __popc(p)];  // j0..j4 are ints 3..7 of the record pair
+                    const int step = __popc(~r0.x & le & ~(0xffffffffu >> (31 - last)));
+                    const int linkidx = P.nAct + (int)r0.z + __popc(r0.x & lt);
+                    const int cq = ((r0.x >> lane) & 1u) ? linkidx : base + step;
+                    nb[d] = cq;
+                    a[OPC(d)] = P.f[OPC(d)][cq];
+                    if (MP) b[OPC(d)] = P.gg[OPC(d)][cq];
+                    // software prefetch into L2 for the warps pf_dist nodes ahead: their neighbour indices differ from
+                    // ours by ~pf_dist (same offsets), one request per 128-byte line
+                    if (P.pf_dist > 0 && (lane & 15) == 0) {
+                        const int pq = min(cq + P.pf_dist, P.nAct - 1);
+                        prefetch_l2(P.f[OPC(d)] + pq);
+                        if (MP) prefetch_l2(P.gg[OPC(d)] + pq);
+                    }
+                }
+                if (P.pf_dist > 0) {
+                    const int wn = min((n + P.pf_dist) >> 5, (P.nA - 1) >> 5);
+                    if (lane < 5) prefetch_l2(reinterpret_cast<const char *>(P.adj + (size_t)wn * MFLBM_ADJ_REC) + 128 * lane);
+                    if (lane == 5) prefetch_l2(P.cellA + min(n + P.pf_dist, P.nA - 1));
+                    if (lane == 6) {
+                        const int pq = min(n + P.pf_dist, P.nA - 1);
+                        prefetch_l2(P.f[0] + pq);
+                        if (MP) prefetch_l2(P.gg[0] + pq);
+                    }
+                }
+            } else {  // warp-uniform and rare: directions with more than five index runs read their indices verbatim
                 const int *__restrict__ row = P.adjfull + (size_t)rec[0].y * 32 + lane;
 #pragma unroll
-                for (int q = 1; q < 19; q++)
-                    if ((irr >> (q - 1)) & 1u) nb[q] = __ldg(row + 32 * __popc(irr & ((1u << (q - 1)) - 1u)));
-            }
-        }
+                for (int d = 1; d < 19; d++) {
+                    int cq = adj_index(rec[1 + 2 * (d - 1)], rec[2 + 2 * (d - 1)], lane, P.nAct);
+                    if ((irr >> (d - 1)) & 1u) cq = __ldg(row + 32 * __popc(irr & ((1u << (d - 1)) - 1u)));
+                    nb[d] = cq;
+                }
 #pragma unroll
-        for (int q = 0; q < 19; q++) {
-            const int cq = SPARSE ? nb[OPC(q)] : c - P.g.off(q);
-            a[q] = P.f[q][cq];
-            if (MP) b[q] = P.gg[q][cq];
+                for (int d = 1; d < 19; d++) {
+                    a[OPC(d)] = P.f[OPC(d)][nb[d]];
+                    if (MP) b[OPC(d)] = P.gg[OPC(d)][nb[d]];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 19; q++) {
+                const int cq = c - P.g.off(q);
+                a[q] = P.f[q][cq];
+                if (MP) b[q] = P.gg[q][cq];
+            }
         }
     } else {  // node-local, direction-swapped slots (MP/Kernel_multiphase.F90:410-448)
         const int cl = SPARSE ? n : c;

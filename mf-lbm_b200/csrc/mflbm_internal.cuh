@@ -92,6 +92,7 @@ struct Dev {
     // verbatim in adjfull, row fullbase + popc(irrmask below d).  72 B/node of int32 indices become ~18.5 B/node.
     uint4 *adj;       // [ceil(nA/32)][37]
     int *adjfull;     // [rows][32]
+    int pf_dist;      // L2 software-prefetch distance of the odd step in nodes (0 = off)
     int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated

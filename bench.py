@@ -210,17 +210,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def allreduce(x, op="sum"):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
-        return float(t.item())
+    rk = import_module("mflbm_b200.dist").Ranks(backend="nccl")  # rendezvous, scalar reductions, NCCL-id broadcast
+    dist = rk.dist
+    allreduce = rk.allreduce
 
     nx, ny, nzG = spec["nx"], spec["ny"], spec["nz"]
     nz = nzG // n_gpus
@@ -243,11 +235,7 @@ def main():
     drv.set_pore_sum(pore_global)
     nccl_id = None
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(M.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
+        nccl_id = rk.broadcast_bytes(M.nccl_unique_id() if rank == 0 else b"", 128)
     drv.create_context(device=local_rank, nccl_unique_id=nccl_id, kernel_variant=args.variant)
     drv.upload(free_host=True)
     if mp:
@@ -344,9 +332,7 @@ def main():
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    rk.close()
     return 0
 
 

@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 dense, 2 sparse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer sweeps: skip the end-to-end leg (the line then has e2e = null)")
     args = ap.parse_args()
     if args.steps % 2:
         args.steps += 1  # AA pattern: keep odd/even parity across rounds like the reference (MP/Main_multiphase.F90:510)
@@ -283,7 +284,7 @@ def main():
     # mflbm_step, and a D2H read of the step's result (saturation partial sums via mflbm_cal_saturation / flow monitor)
     w_in = torch.zeros((ny + 2) * (nx + 2), dtype=torch.float64).pin_memory()
     w_in.copy_(torch.from_numpy(np.ascontiguousarray(drv.field("w_in").ravel(order="F"))))
-    e2e_steps = args.steps
+    e2e_steps = 0 if args.no_e2e else args.steps
     barrier()
     t0 = time.perf_counter()
     drv.timer_start()
@@ -300,7 +301,7 @@ def main():
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = allreduce(max(ms_e2e, 0.0), "max")
-    e2e_mlups = pore_global * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    e2e_mlups = pore_global * e2e_steps / (ms_e2e * 1e-3) / 1e6 if e2e_steps else None
     h2d = (nx + 2) * (ny + 2) * 8
     d2h = 2 * nz * 8 if mp else 0
 
@@ -320,8 +321,8 @@ def main():
                          "traffic": traffic, "kernel": "k_collide (collision + AA streaming)", "peak_source": peak_src,
                          "bytes_per_update": bpu, "kernel_ms_per_step": coll_ms / args.steps, "kernel_launches": coll_launches,
                          "step_frac_of_roofline": mlups * 1e6 * bpu / 1e9 / (peak * n_gpus)},
-            "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / e2e_steps, "host_wall_ms_per_step": wall_e2e / e2e_steps,
+            "e2e": None if args.no_e2e else {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / max(e2e_steps, 1), "host_wall_ms_per_step": wall_e2e / max(e2e_steps, 1),
                     "what": "per step: mflbm_upload(w_in, pinned host) + mflbm_step + mflbm_cal_saturation read-back"},
             "gpu_launches": int(launches), "clocks": clocks}
     drv.close()

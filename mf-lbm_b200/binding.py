@@ -71,7 +71,11 @@ def load(strict=False):
     key = bool(strict)
     if key in _LIBS:
         return _LIBS[key]
-    path = os.path.join(LIB_DIR, "libmflbm_strict.so" if strict else "libmflbm.so")
+    # MFLBM_LIB_VARIANT=name selects an experimental build of the same sources (make variant NAME=name EXTRA=...):
+    # used by tools/sweep.sh to compare kernel tunings in one GPU session
+    variant = os.environ.get("MFLBM_LIB_VARIANT", "")
+    name = "libmflbm_strict.so" if strict else ("libmflbm_%s.so" % variant if variant else "libmflbm.so")
+    path = os.path.join(LIB_DIR, name)
     if not os.path.exists(path):
         raise MflbmError("%s not built: run __graft_entry__.build() (there is no CPU fallback)" % path)
     lib = C.CDLL(path)

@@ -258,6 +258,21 @@ __global__ void k_tile_update(const Dev P, int cur, int stamp) {
     }
 }
 
+// Stamp every warp of 32 consecutive A nodes that owns a fluid node of ACTIVE tile `tile` (called by the 64 threads of
+// a K4 block, two cells per thread).  Warps left with a stale stamp lie entirely in quiet tiles: the collision kernel
+// knows |grad phi| = 0 there without reading anything (see Dev::wstamp).
+__device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int stamp) {
+    const int tx = tile % P.ntx, ty = (tile / P.ntx) % P.nty, tz = tile / (P.ntx * P.nty);
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const int e = threadIdx.x + 64 * m;  // cell of the 8x4x4 tile
+        const int ix = 8 * tx + (e & 7), jy = 4 * ty + ((e >> 3) & 3), kz = 4 * tz + (e >> 5);
+        if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
+        const int a = P.smap[P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz];
+        if (a >= 0 && a < P.nA) P.wstamp[a >> 5] = stamp;
+    }
+}
+
 // every tile active (explicit mflbm_color_gradient)
 __global__ void k_tile_all(const Dev P) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,12 +287,13 @@ __global__ void k_tile_all(const Dev P) {
 
 // tile-driven launch shape: persistent blocks walk a tile list; the threads of a block share the entries of one tile
 template <int K>
-__global__ void __launch_bounds__(64) k_chain_tiles(const Dev P) {
+__global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp) {
     const int *__restrict__ list = K == 3 ? P.tk3 : P.tact;
     const int count = P.tcount[K == 3 ? 1 : 0];
     const int *__restrict__ start = (K == 3 || K == 6) ? P.ts_start : (K == 4 ? P.tg_start : P.tf_start);
     for (int t = blockIdx.x; t < count; t += gridDim.x) {
         const int tile = list[t];
+        if (K == 4 && stamp > 0) tile_stamp_warps(P, tile, stamp);
         const int e1 = start[tile + 1];
         for (int e = start[tile] + threadIdx.x; e < e1; e += 64) {
             if (K == 3) phi_solid_at(P, e);
@@ -290,8 +306,9 @@ __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P) {
 
 // every tile active: after create / upload / compute_macro_vars / an explicit mflbm_color_gradient
 void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st) {
-    const Dev &P = c->d;
+    Dev &P = c->d;
     if (!P.use_tiles) return;
+    P.wq_all = 1;
     const size_t n = (size_t)P.ntiles + 4;
     cudaMemsetAsync(P.tcls[0], 0, n, st);
     cudaMemsetAsync(P.tcls[1], 0, n, st);
@@ -309,6 +326,7 @@ int tiles_prepare(mflbm_ctx *c, cudaStream_t st) {
     cudaMemsetAsync(mark, 0, (size_t)P.g.ntot, st);
     cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles + 4, st);
     cudaMemsetAsync(P.tk3stamp, 0, (size_t)P.ntiles * sizeof(int), st);
+    cudaMemsetAsync(P.wstamp, 0, ((size_t)(P.nA + 31) / 32 + 1) * sizeof(int), st);
     if (P.num_solid > 0) {
         k_tile_mark_solid<<<(P.num_solid + 255) / 256, 256, 0, st>>>(P, mark);
         c->launches++;
@@ -343,6 +361,8 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
         if (stepping) {
             cudaMemsetAsync(P.tcount, 0, 2 * sizeof(int), st);
             k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp);
+            P.wq_stamp = c->tile_stamp;
+            P.wq_all = 0;
             P.tile_cur ^= 1;
             c->solid_phi_stale = true;
         } else {
@@ -351,10 +371,11 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
             c->solid_phi_stale = false;
         }
         const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
-        if (P.num_solid > 0) k_chain_tiles<3><<<grid, 64, 0, st>>>(P);
-        if (P.nG > 0) k_chain_tiles<4><<<grid, 64, 0, st>>>(P);
-        if (P.num_fluid > 0) k_chain_tiles<5><<<grid, 64, 0, st>>>(P);
-        if (P.num_solid > 0) k_chain_tiles<6><<<grid, 64, 0, st>>>(P);
+        // K4 also stamps the warps of the active tiles (stepping only; nG > 0 whenever there is a fluid node)
+        if (P.num_solid > 0) k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0);
+        if (P.nG > 0) k_chain_tiles<4><<<grid, 64, 0, st>>>(P, stepping ? c->tile_stamp : 0);
+        if (P.num_fluid > 0) k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0);
+        if (P.num_solid > 0) k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0);
         c->launches += 1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0);
         return;
     }

@@ -137,25 +137,42 @@ void launch_monitor(mflbm_ctx *c, cudaStream_t st, double *out) {
     c->launches++;
 }
 
-// cal_saturation: out rows v1, v2
+// cal_saturation: out rows v1, v2, each nz * MFLBM_SAT_SEG partial sums (slice k, segment s at [row][k - 1 + nz * s]); the
+// host adds them up.  One warp per row of the slice (coalesced, no index division), MFLBM_SAT_SEG blocks per slice so
+// that a 512-slice lattice fills the 148 SMs more than once.
 __global__ void __launch_bounds__(256) k_saturation(const Dev P, double *out) {
     const int k = blockIdx.x + 1;
     const int nx = P.g.nx, ny = P.g.ny;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double v[2] = {0, 0};
-    for (int n = threadIdx.x; n < nx * ny; n += blockDim.x) {
-        const int j = n / nx + 1, i = n - (j - 1) * nx + 1;
-        const int c = P.g.cell(i, j, k);
-        const int wi = P.walls[c];
-        const double ph = P.phi[c];
-        v[0] += 0.5 * (1.0 + ph) * (1 - wi);
-        v[1] += 0.5 * (1.0 - ph) * (1 - wi);
+    for (int j = 1 + blockIdx.y * 8 + wid; j <= ny; j += 8 * gridDim.y) {
+        const int c0 = P.g.cell(1, j, k);
+        for (int i = lane; i < nx; i += 32) {
+            const int wi = P.walls[c0 + i];
+            const double ph = P.phi[c0 + i];
+            v[0] += 0.5 * (1.0 + ph) * (1 - wi);
+            v[1] += 0.5 * (1.0 - ph) * (1 - wi);
+        }
     }
-    const bool is_max[2] = {false, false};
-    block_reduce<2>(v, is_max, out, P.g.nz, 0);
+    __shared__ double sm[2][8];
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+        double x = v[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[n][wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int n = threadIdx.x;
+        double x = sm[n][0];
+        for (int w = 1; w < 8; w++) x += sm[n][w];
+        out[(size_t)n * P.g.nz * gridDim.y + blockIdx.x + (size_t)P.g.nz * blockIdx.y] = x;
+    }
 }
 
 void launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out) {
-    k_saturation<<<c->d.g.nz, 256, 0, st>>>(c->d, out);
+    k_saturation<<<dim3(c->d.g.nz, MFLBM_SAT_SEG), 256, 0, st>>>(c->d, out);
     c->launches++;
 }
 

@@ -19,73 +19,104 @@ namespace mflbm {
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <bool MP, bool ODD, bool SPARSE>
-__global__ void __launch_bounds__(128, 4) k_collide(const Dev P, int k0, int n0, int n1) {
-    int c, n = 0;
-    __shared__ uint4 s_adj[SPARSE && ODD ? 4 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
-    if (SPARSE) {
-        // n0 is rounded down to a multiple of 32 by the launcher so that lane == n & 31 (the adjacency is per warp of
-        // 32 consecutive A nodes)
-        n = (n0 & ~31) + blockIdx.x * blockDim.x + threadIdx.x;
-        if (ODD) {
-            // stage this warp's 37 adjacency records (592 contiguous bytes) in shared memory with one coalesced load
-            // wave; decoding them straight from global memory makes ptxas chain 18 load->use round trips (measured)
-            const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-            if ((n & ~31) < n1) {
-                const uint4 *__restrict__ rec = P.adj + (size_t)(n >> 5) * MFLBM_ADJ_REC;
-                s_adj[wib][lane] = __ldg(rec + lane);
-                if (lane < MFLBM_ADJ_REC - 32) s_adj[wib][32 + lane] = __ldg(rec + 32 + lane);
-            }
-            __syncwarp();
+__device__ __forceinline__ double ldpop(const double *p) { return *p; }
+__device__ __forceinline__ void stpop(double *p, double v) { *p = v; }
+
+// resident blocks of 128 threads per SM the register allocation is bounded for (4 -> 128 registers, 5 -> 96, 6 -> 80)
+#ifndef MFLBM_MP_BLOCKS
+#define MFLBM_MP_BLOCKS 4
+#endif
+#ifndef MFLBM_SP_BLOCKS
+#define MFLBM_SP_BLOCKS 5  // measured on C2: 5 blocks (96 registers, 16-40 B of spills) +1 % over 4, 6 blocks -6 %
+#endif
+
+// Collision of one node in registers (a = fluid 1 / the single fluid, b = fluid 2), including what surrounds it on the
+// multiphase path: interface normal / curvature inputs, the phi store and the per-tile phi classes.
+template <bool MP, bool SPARSE>
+__device__ __forceinline__ void collide_node(const Dev &P, const int c, const int wst, double (&a)[19], double (&b)[19]) {
+    if (MP) {
+        // c_norm == 0 (no interface nearby: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature) lets the sparse
+        // layout skip the normal loads and the curvature stencil.  Exact: the skipped terms are +-0.
+        // Quiet tile (uniform phi around, see kernels_gradient.cu): c_norm is known to be 0 without reading it.
+        const bool quiet = SPARSE && P.use_tiles && !P.wq_all && wst != P.wq_stamp;  // warp-uniform
+        const double c_norm = quiet ? 0.0 : P.c_norm[c];
+        double cnx = 0.0, cny = 0.0, cnz = 0.0, curv = 0.0;
+        if (!SPARSE) {
+            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c]; curv = P.curv[c];
+        } else if (c_norm != 0.0) {
+            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
+            curv = curvature_at(P, c);  // K7 evaluated here from the neighbours' normals instead of a stored field
         }
-        if (n < n0 || n >= n1) return;
-        c = P.cellA[n];
+        const double phi = collide_mp(P, a, b, cnx, cny, cnz, curv, c_norm);
+        P.phi[c] = phi;
+        if (SPARSE && P.use_tiles) {
+            // record the phi class of this node's tile: consecutive lanes mostly share (tile, class), so the first lane
+            // of every run of equal keys issues one fire-and-forget atomic (a handful per warp)
+            const int tile = P.g.tile_of(c, P.ntx, P.nty);
+            const unsigned bits = fabs(phi - 1.0) <= 1e-7 ? 1u : (fabs(phi + 1.0) <= 1e-7 ? 2u : 4u);
+            const unsigned key = ((unsigned)tile << 3) | bits;
+            const unsigned act = __activemask();
+            const unsigned prev = __shfl_up_sync(act, key, 1);
+            const int lane = threadIdx.x & 31;
+            if (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != key)
+                atomicOr((unsigned *)(P.tcls[P.tile_cur] + (tile & ~3)), bits << (8 * (tile & 3)));
+        }
     } else {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-        const int j = blockIdx.y + 1;
-        const int k = blockIdx.z + k0;
-        if (i > P.g.nx) return;
-        c = P.g.cell(i, j, k);
-        if (P.walls[c] != 0) return;
+        collide_sp(P, a);
     }
 
+}
+
+// Neighbour indices of the sparse odd step for this lane's node from the warp's adjacency records (shared memory).
+__device__ __forceinline__ void decode_nb(const Dev &P, const uint4 *rec, const int lane, int (&nb)[19]) {
+    const int *reci = reinterpret_cast<const int *>(rec);
+    const unsigned irr = rec[0].x;
+    if (irr == 0) {
+#pragma unroll
+        for (int d = 1; d < 19; d++) nb[d] = adj_index_fast(reci, d, lane, P.nAct);
+    } else {  // warp-uniform and rare
+        const int *__restrict__ row = P.adjfull + (size_t)rec[0].y * 32 + lane;
+#pragma unroll
+        for (int d = 1; d < 19; d++) {
+            int cq = adj_index(rec[1 + 2 * (d - 1)], rec[2 + 2 * (d - 1)], lane, P.nAct);
+            if ((irr >> (d - 1)) & 1u) cq = __ldg(row + 32 * __popc(irr & ((1u << (d - 1)) - 1u)));
+            nb[d] = cq;
+        }
+    }
+}
+
+// One node: gather the incoming populations, collide, scatter.  n = active index (sparse layout), c = dense cell,
+// wst = this warp's quiet stamp (Dev::wstamp), rec = this warp's adjacency records in shared memory (sparse odd step).
+template <bool MP, bool ODD, bool SPARSE, bool PF>
+__device__ __forceinline__ void node_update(const Dev &P, const int n, const int c, const int wst, const uint4 *rec) {
     double a[19], b[19];
     int nb[19];  // sparse odd step: active index of x+e_q
     if (ODD) {   // pull f_q from x - e_q (MP/Kernel_multiphase.F90:46-84)
         if (SPARSE) {
             nb[0] = n;
-            a[0] = P.f[0][n];
-            if (MP) b[0] = P.gg[0][n];
-            const uint4 *rec = s_adj[threadIdx.x >> 5];
+            a[0] = ldpop(&P.f[0][n]);
+            if (MP) b[0] = ldpop(&P.gg[0][n]);
             const int *reci = reinterpret_cast<const int *>(rec);
             const int lane = n & 31;
-            const unsigned le = 0xffffffffu >> (31 - lane), lt = le >> 1;
             const unsigned irr = rec[0].x;
             if (irr == 0) {
                 // decode direction d and issue its population loads right away, so that the memory system is busy while
-                // the remaining directions are decoded (pure LDS + ALU, ~16 instructions each)
+                // the remaining directions are decoded (pure LDS + ALU, ~10 instructions each)
 #pragma unroll
                 for (int d = 1; d < 19; d++) {
-                    const uint4 r0 = rec[1 + 2 * (d - 1)];
-                    unsigned p = r0.y & le;
-                    p = p ? p : 1u;
-                    const int last = 31 - __clz(p);
-                    const int base = reci[4 * (1 + 2 * (d - 1)) + 2 + __popc(p)];  // j0..j4 are ints 3..7 of the record pair
-                    const int step = __popc(~r0.x & le & ~(0xffffffffu >> (31 - last)));
-                    const int linkidx = P.nAct + (int)r0.z + __popc(r0.x & lt);
-                    const int cq = ((r0.x >> lane) & 1u) ? linkidx : base + step;
+                    const int cq = adj_index_fast(reci, d, lane, P.nAct);
                     nb[d] = cq;
-                    a[OPC(d)] = P.f[OPC(d)][cq];
-                    if (MP) b[OPC(d)] = P.gg[OPC(d)][cq];
+                    a[OPC(d)] = ldpop(&P.f[OPC(d)][cq]);
+                    if (MP) b[OPC(d)] = ldpop(&P.gg[OPC(d)][cq]);
                     // software prefetch into L2 for the warps pf_dist nodes ahead: their neighbour indices differ from
                     // ours by ~pf_dist (same offsets), one request per 128-byte line
-                    if (P.pf_dist > 0 && (lane & 15) == 0) {
+                    if (PF && (lane & 15) == 0) {
                         const int pq = min(cq + P.pf_dist, P.nAct - 1);
                         prefetch_l2(P.f[OPC(d)] + pq);
                         if (MP) prefetch_l2(P.gg[OPC(d)] + pq);
                     }
                 }
-                if (P.pf_dist > 0) {
+                if (PF) {
                     const int wn = min((n + P.pf_dist) >> 5, (P.nA - 1) >> 5);
                     if (lane < 5) prefetch_l2(reinterpret_cast<const char *>(P.adj + (size_t)wn * MFLBM_ADJ_REC) + 128 * lane);
                     if (lane == 5) prefetch_l2(P.cellA + min(n + P.pf_dist, P.nA - 1));
@@ -113,68 +144,208 @@ __global__ void __launch_bounds__(128, 4) k_collide(const Dev P, int k0, int n0,
 #pragma unroll
             for (int q = 0; q < 19; q++) {
                 const int cq = c - P.g.off(q);
-                a[q] = P.f[q][cq];
-                if (MP) b[q] = P.gg[q][cq];
+                a[q] = ldpop(&P.f[q][cq]);
+                if (MP) b[q] = ldpop(&P.gg[q][cq]);
             }
         }
     } else {  // node-local, direction-swapped slots (MP/Kernel_multiphase.F90:410-448)
         const int cl = SPARSE ? n : c;
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            a[q] = P.f[OPC(q)][cl];
-            if (MP) b[q] = P.gg[OPC(q)][cl];
+            a[q] = ldpop(&P.f[OPC(q)][cl]);
+            if (MP) b[q] = ldpop(&P.gg[OPC(q)][cl]);
         }
     }
 
-    if (MP) {
-        // c_norm == 0 (no interface nearby: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature) lets the sparse
-        // layout skip the normal loads and the curvature stencil.  Exact: the skipped terms are +-0.
-        // Quiet tile (uniform phi around, see kernels_gradient.cu): c_norm is known to be 0 without reading it.
-        int tile = 0;
-        bool quiet = false;
-        if (SPARSE && P.use_tiles) {
-            tile = P.g.tile_of(c, P.ntx, P.nty);
-            quiet = P.tquiet[tile] != 0;
-        }
-        const double c_norm = quiet ? 0.0 : P.c_norm[c];
-        double cnx = 0.0, cny = 0.0, cnz = 0.0, curv = 0.0;
-        if (!SPARSE) {
-            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c]; curv = P.curv[c];
-        } else if (c_norm != 0.0) {
-            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
-            curv = curvature_at(P, c);  // K7 evaluated here from the neighbours' normals instead of a stored field
-        }
-        const double phi = collide_mp(P, a, b, cnx, cny, cnz, curv, c_norm);
-        P.phi[c] = phi;
-        if (SPARSE && P.use_tiles) {  // record the phi class of this node's tile: one atomic per (warp, tile, class)
-            const unsigned bits = fabs(phi - 1.0) <= 1e-7 ? 1u : (fabs(phi + 1.0) <= 1e-7 ? 2u : 4u);
-            const unsigned key = ((unsigned)tile << 3) | bits;
-            const unsigned peers = __match_any_sync(__activemask(), key);
-            if ((threadIdx.x & 31) == __ffs(peers) - 1)
-                atomicOr((unsigned *)(P.tcls[P.tile_cur] + (tile & ~3)), bits << (8 * (tile & 3)));
-        }
-    } else {
-        collide_sp(P, a);
-    }
+    collide_node<MP, SPARSE>(P, c, wst, a, b);
 
     if (ODD) {  // push q into slot opc(q) of x + e_q (MP/Kernel_multiphase.F90:318-354)
         const int cl = SPARSE ? n : c;
-        P.f[0][cl] = a[0];
-        if (MP) P.gg[0][cl] = b[0];
+        stpop(&P.f[0][cl], a[0]);
+        if (MP) stpop(&P.gg[0][cl], b[0]);
 #pragma unroll
         for (int q = 1; q < 19; q++) {
             const int cq = SPARSE ? nb[q] : c + P.g.off(q);
-            P.f[OPC(q)][cq] = a[q];
-            if (MP) P.gg[OPC(q)][cq] = b[q];
+            stpop(&P.f[OPC(q)][cq], a[q]);
+            if (MP) stpop(&P.gg[OPC(q)][cq], b[q]);
         }
     } else {
         const int cl = SPARSE ? n : c;
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            P.f[q][cl] = a[q];
-            if (MP) P.gg[q][cl] = b[q];
+            stpop(&P.f[q][cl], a[q]);
+            if (MP) stpop(&P.gg[q][cl], b[q]);
         }
     }
+}
+
+template <bool MP, bool ODD, bool SPARSE, bool PF = false>
+__global__ void __launch_bounds__(128, MP ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) k_collide(const Dev P, int k0, int n0, int n1) {
+    int c, n = 0, wst = 0;
+    __shared__ uint4 s_adj[SPARSE && ODD ? 4 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
+    if (SPARSE) {
+        // n0 is rounded down to a multiple of 32 by the launcher so that lane == n & 31 (the adjacency is per warp of
+        // 32 consecutive A nodes)
+        n = (n0 & ~31) + blockIdx.x * blockDim.x + threadIdx.x;
+        if (ODD) {
+            // stage this warp's 37 adjacency records (592 contiguous bytes) in shared memory with one coalesced load
+            // wave; decoding them straight from global memory makes ptxas chain 18 load->use round trips (measured)
+            const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+            if ((n & ~31) < n1) {
+                const uint4 *__restrict__ rec = P.adj + (size_t)(n >> 5) * MFLBM_ADJ_REC;
+                s_adj[wib][lane] = __ldg(rec + lane);
+                if (lane < MFLBM_ADJ_REC - 32) s_adj[wib][32 + lane] = __ldg(rec + 32 + lane);
+            }
+            __syncwarp();
+        }
+        if (n < n0 || n >= n1) return;
+        c = P.cellA[n];
+        if (MP) wst = P.use_tiles ? P.wstamp[n >> 5] : 0;
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+        const int j = blockIdx.y + 1;
+        const int k = blockIdx.z + k0;
+        if (i > P.g.nx) return;
+        c = P.g.cell(i, j, k);
+        if (P.walls[c] != 0) return;
+    }
+
+    node_update<MP, ODD, SPARSE, PF>(P, n, c, wst, SPARSE && ODD ? s_adj[threadIdx.x >> 5] : nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pipelined, persistent flavour of the sparse kernels (Dev::pipe: 1 = odd step, 2 = odd and even steps).  The register file caps the collision kernel at 16 warps
+// per SM, and a warp that gathers its 38 populations into registers has nothing in flight while it collides and
+// scatters.  Here every warp owns a shared-memory stage of 38 x 32 doubles: while batch i is collided out of registers,
+// the populations of batch i+1 are already being gathered into the stage with cp.async (8-byte elements: neighbour runs
+// are not 16-byte aligned), and the adjacency records of batch i+2 into the other half of a double buffer.  The AA
+// pattern makes this legal: a node reads and writes the same 38 addresses and no two nodes share an address, so
+// reading batch i+1 before batch i is written back cannot observe batch i's results.  In-flight bytes per SM no longer
+// depend on the register allocation (16 warps x 9.7 KB).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define MFLBM_ADJ_STAGE 40  // uint4 per adjacency buffer (37 used; keeps the buffers 128-byte granular)
+
+template <bool MP, bool ODD>
+__global__ void __launch_bounds__(128, MP ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) k_collide_pipe(const Dev P, int n0, int n1) {
+    constexpr int NP = MP ? 38 : 19;
+    constexpr int WARP_BYTES = NP * 32 * 8 + (ODD ? 2 * MFLBM_ADJ_STAGE * 16 : 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)wib * WARP_BYTES;
+    const double *pop = reinterpret_cast<const double *>(wbase);
+    const uint4 *adjb = reinterpret_cast<const uint4 *>(wbase + NP * 32 * 8);
+    const unsigned pop_s = (unsigned)__cvta_generic_to_shared(wbase) + 8u * lane;
+    const unsigned adj_s = (unsigned)__cvta_generic_to_shared(wbase + NP * 32 * 8) + 16u * lane;
+    const int W = gridDim.x * 4;
+    const int wb1 = (n1 + 31) >> 5;
+    int wb = (n0 >> 5) + blockIdx.x * 4 + wib;
+    if (wb >= wb1) return;
+
+    auto fetch_adj = [&](int w, int buf) {  // one commit group, possibly empty
+        if (ODD && w < wb1) {
+            const uint4 *__restrict__ src = P.adj + (size_t)w * MFLBM_ADJ_REC;
+            const unsigned dst = adj_s + 16u * MFLBM_ADJ_STAGE * buf;
+            cp_async16(dst, src + lane);
+            if (lane < MFLBM_ADJ_REC - 32) cp_async16(dst + 16u * 32, src + 32 + lane);
+        }
+        cp_async_commit();
+    };
+    auto gather = [&](int w, int buf) {  // populations of batch w -> stage; one commit group, possibly empty
+        const int n = w * 32 + lane;
+        if (w < wb1 && n >= n0 && n < n1) {
+            if (ODD) {
+                int nb[19];
+                nb[0] = n;
+                decode_nb(P, adjb + MFLBM_ADJ_STAGE * buf, lane, nb);
+#pragma unroll
+                for (int d = 0; d < 19; d++) {
+                    cp_async8(pop_s + 256u * OPC(d), P.f[OPC(d)] + nb[d]);
+                    if (MP) cp_async8(pop_s + 256u * (19 + OPC(d)), P.gg[OPC(d)] + nb[d]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 19; q++) {
+                    cp_async8(pop_s + 256u * q, P.f[OPC(q)] + n);
+                    if (MP) cp_async8(pop_s + 256u * (19 + q), P.gg[OPC(q)] + n);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    fetch_adj(wb, 0);
+    if (ODD) {
+        cp_async_wait<0>();
+        __syncwarp();
+    }
+    gather(wb, 0);
+    fetch_adj(wb + W, 1);
+    for (int buf = 0; wb < wb1; wb += W, buf ^= 1) {
+        const int n = wb * 32 + lane;
+        const bool valid = n >= n0 && n < n1;
+        int c = 0, wst = 0;
+        if (valid) {
+            c = P.cellA[n];
+            if (MP && P.use_tiles) wst = P.wstamp[wb];
+        }
+        cp_async_wait<1>();  // everything but the newest group (the adjacency fetch): this batch's populations are in
+        __syncwarp();
+        double a[19], b[19];
+        int nb[19];
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 19; q++) {
+                a[q] = pop[q * 32 + lane];
+                if (MP) b[q] = pop[(19 + q) * 32 + lane];
+            }
+            if (ODD) {
+                nb[0] = n;
+                decode_nb(P, adjb + MFLBM_ADJ_STAGE * buf, lane, nb);
+            }
+        }
+        if (ODD) cp_async_wait<0>();  // adjacency of the next batch (issued one iteration ago)
+        __syncwarp();                 // stage and adjacency buffer `buf` are consumed by every lane
+        gather(wb + W, buf ^ 1);
+        fetch_adj(wb + 2 * W, buf);
+        if (valid) {
+            collide_node<MP, true>(P, c, wst, a, b);
+            if (ODD) {  // push q into slot opc(q) of x + e_q
+#pragma unroll
+                for (int q = 0; q < 19; q++) {
+                    stpop(&P.f[OPC(q)][nb[q]], a[q]);
+                    if (MP) stpop(&P.gg[OPC(q)][nb[q]], b[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 19; q++) {
+                    stpop(&P.f[q][n], a[q]);
+                    if (MP) stpop(&P.gg[q][n], b[q]);
+                }
+            }
+        }
+    }
+}
+
+template <bool MP, bool ODD>
+static void launch_pipe(const Dev &P, cudaStream_t st, int resident, int n0, int n1) {
+    constexpr int bytes = 4 * ((MP ? 38 : 19) * 32 * 8 + (ODD ? 2 * MFLBM_ADJ_STAGE * 16 : 0));
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_collide_pipe<MP, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaFuncSetAttribute(k_collide_pipe<MP, ODD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    k_collide_pipe<MP, ODD><<<resident, 128, bytes, st>>>(P, n0, n1);
 }
 
 template <bool SPARSE>
@@ -187,14 +358,29 @@ static void launch_collide_t(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, in
         n1 = c->kstartA[k1 + 1];
         if (n1 <= n0) return;
         grid = dim3((n1 - (n0 & ~31) + 127) / 128);
+        const int resident = P.pipe_grid > 0 ? P.pipe_grid : 148 * (P.multiphase ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS);
+        if (P.pipe && (odd || P.pipe >= 2) && (int)grid.x > resident) {
+            if (P.multiphase) {
+                if (odd) launch_pipe<true, true>(P, st, resident, n0, n1);
+                else launch_pipe<true, false>(P, st, resident, n0, n1);
+            } else {
+                if (odd) launch_pipe<false, true>(P, st, resident, n0, n1);
+                else launch_pipe<false, false>(P, st, resident, n0, n1);
+            }
+            c->launches++;
+            return;
+        }
     } else {
         grid = dim3((P.g.nx + 127) / 128, P.g.ny, k1 - k0 + 1);
     }
+    const bool pf = SPARSE && odd && P.pf_dist > 0;  // L2 software prefetch: a separate instantiation, no dead issue slots
     if (P.multiphase) {
-        if (odd) k_collide<true, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        if (pf) k_collide<true, true, SPARSE, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        else if (odd) k_collide<true, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else k_collide<true, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     } else {
-        if (odd) k_collide<false, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        if (pf) k_collide<false, true, SPARSE, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        else if (odd) k_collide<false, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else k_collide<false, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     }
     c->launches++;
@@ -287,9 +473,8 @@ void launch_fill_smap(mflbm_ctx *c, cudaStream_t st) {
 // caller's (0:nx+1,0:ny+1,0:nz+1) array <-> active-node list
 // position of dense cell c in the caller's (0:nx+1,0:ny+1,0:nz+1) array
 __device__ __forceinline__ size_t host_pos(const Dev &P, int c) {
-    const unsigned r = (unsigned)(c - (P.g.base - 4));  // (i+3) + sx*(j+3) + sxy*(k+3)
-    const unsigned kz = r / (unsigned)P.g.sxy, r2 = r - kz * (unsigned)P.g.sxy;
-    const unsigned jy = r2 / (unsigned)P.g.sx, ix = r2 - jy * (unsigned)P.g.sx;
+    unsigned ix, jy, kz;
+    P.g.coords3(c, ix, jy, kz);
     return (size_t)(ix - 3) + (size_t)(P.g.nx + 2) * ((size_t)(jy - 3) + (size_t)(P.g.ny + 2) * (size_t)(kz - 3));
 }
 

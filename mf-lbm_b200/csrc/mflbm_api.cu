@@ -193,6 +193,7 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         Dev &d = ctx->d;
         d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
         d.g.sx = (int)sx; d.g.sxy = (int)sxy; d.g.base = 16; d.g.ntot = (int)ntot;
+        d.g.set_magic();
         d.multiphase = cfg->solver == MFLBM_SOLVER_MULTIPHASE;
         d.mrt = cfg->mrt;
         d.la_nui1 = cfg->la_nui1; d.la_nui2 = cfg->la_nui2; d.gamma = cfg->gamma; d.beta = cfg->beta;
@@ -446,7 +447,7 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
                 if (irregular) full[(size_t)row * 32 + l] = v;
                 if (v != prev + 1) {
                     jmask |= 1u << l;
-                    if (jumps < 5) inl[jumps] = v;
+                    if (jumps < 5) inl[jumps] = v - (l - links);  // B_r = first index - rank of the first lane
                     jumps++;
                 }
                 prev = v;
@@ -464,7 +465,10 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
         for (int n = 0; n < nA; n++) {
             const int w = n >> 5, l = n & 31;
             for (int q = 1; q < 19; q++) {
-                const int got = adj_lookup(&adj[(size_t)w * MFLBM_ADJ_REC], full.data(), q, l, (int)nAct);
+                const uint4 *rec = &adj[(size_t)w * MFLBM_ADJ_REC];
+                const int got = adj_lookup(rec, full.data(), q, l, (int)nAct);
+                // the collision kernel's fast path must agree wherever it is taken (warps without irregular directions)
+                if (rec[0].x == 0) bad += (adj_index_fast(reinterpret_cast<const int *>(rec), q, l, (int)nAct) != got);
                 const int v = nbr_of(n, q);
                 if (v >= 0) bad += (got != v);
                 else bad += (got < nAct || got >= nAct + H.nlink[q]);  // a link slot of direction q
@@ -534,10 +538,15 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
     d.nA = nA;
     d.nAct = (int)nAct;
     {
-        // L2 software prefetch of the odd step, in nodes ahead (about one wave of resident warps; measured on B200:
-        // +3..4 % MLUPS at 65536, -5 % at 262144); MFLBM_PF_DIST=0 switches it off
+        // L2 software prefetch of the odd step, in nodes ahead (about one wave of resident warps).  Measured on B200 with
+        // the compressed adjacency: singlephase C2 +5 % MLUPS at 65536; multiphase C3 -3 % (the extra issue slots cost
+        // more than the L2 hits return), so it is off there.  MFLBM_PF_DIST overrides.
         const char *e = getenv("MFLBM_PF_DIST");
-        d.pf_dist = e ? atoi(e) : 65536;
+        d.pf_dist = e ? atoi(e) : (d.multiphase ? 0 : 65536);
+        e = getenv("MFLBM_PIPE");
+        d.pipe = e ? atoi(e) : 0;
+        e = getenv("MFLBM_PIPE_GRID");
+        d.pipe_grid = e ? atoi(e) : 0;
     }
     if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.adj, adj.size(), false) ||
         dev_alloc(ctx, &d.adjfull, full.size(), false) || dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))
@@ -588,12 +597,21 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     if (d.sparse) {
         if (build_active_set(ctx, walls)) return MFLBM_ERR_CUDA;
         n = (size_t)d.nAct + 64;
+        if (d.use_tiles && dev_alloc(ctx, &d.wstamp, (size_t)(d.nA + 31) / 32 + 1)) return MFLBM_ERR_CUDA;
+        d.wq_all = 1;
     }
     for (int q = 0; q < 19; q++) {
         // sparse: array q also holds the compact link slots of direction opc(q) behind the node entries
         const size_t nq = d.sparse ? n + (size_t)d.nlink[OPC(q)] : n;
-        if (dev_alloc(ctx, &d.f[q], nq)) return MFLBM_ERR_CUDA;
-        if (d.multiphase && dev_alloc(ctx, &d.gg[q], nq)) return MFLBM_ERR_CUDA;
+        // cudaMalloc hands out 2 MiB-aligned blocks, so element n of all 38 arrays would share its low address bits;
+        // MFLBM_ARRAY_SKEW (bytes, multiple of 256) staggers the array bases (experiment: L2 set conflicts of 76 streams)
+        static const size_t skew = getenv("MFLBM_ARRAY_SKEW") ? (size_t)atol(getenv("MFLBM_ARRAY_SKEW")) / 8 : 0;
+        if (dev_alloc(ctx, &d.f[q], nq + 38 * skew)) return MFLBM_ERR_CUDA;
+        d.f[q] += (size_t)q * skew;
+        if (d.multiphase) {
+            if (dev_alloc(ctx, &d.gg[q], nq + 38 * skew)) return MFLBM_ERR_CUDA;
+            d.gg[q] += (size_t)(19 + q) * skew;
+        }
     }
     ctx->pdf_alloc = true;
     return 0;
@@ -1012,9 +1030,10 @@ extern "C" int mflbm_cal_saturation(mflbm_ctx *ctx, double *v1, double *v2) {
     CU(cudaSetDevice(ctx->device));
     const int nz = ctx->cfg.nz;
     launch_saturation(ctx, ctx->s_main, ctx->red_dev);
-    if (check_launch(ctx) || fetch_red(ctx, 2 * nz)) return MFLBM_ERR_CUDA;
+    const int np = nz * MFLBM_SAT_SEG;
+    if (check_launch(ctx) || fetch_red(ctx, 2 * np)) return MFLBM_ERR_CUDA;
     double a = 0, b = 0;
-    for (int k = 0; k < nz; k++) { a += ctx->red_host[k]; b += ctx->red_host[nz + k]; }
+    for (int k = 0; k < np; k++) { a += ctx->red_host[k]; b += ctx->red_host[np + k]; }
     *v1 = a; *v2 = b;
     return MFLBM_OK;
 }
@@ -1158,6 +1177,7 @@ extern "C" int mflbmx_adjacency_selftest(int nx, int ny, int nz, const int8_t *w
     g.sxy = g.sx * (ny + 8);
     g.base = 16;
     g.ntot = 16 + g.sxy * (nz + 8) + 16;
+    g.set_magic();
     HostActive H;
     std::string err;
     if (build_active_host(g, walls, H, err, true)) {

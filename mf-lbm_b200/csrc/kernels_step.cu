@@ -67,27 +67,9 @@ __device__ __forceinline__ void collide_node(const Dev &P, const int c, const in
 
 }
 
-// Neighbour indices of the sparse odd step for this lane's node from the warp's adjacency records (shared memory).
-__device__ __forceinline__ void decode_nb(const Dev &P, const uint4 *rec, const int lane, int (&nb)[19]) {
-    const int *reci = reinterpret_cast<const int *>(rec);
-    const unsigned irr = rec[0].x;
-    if (irr == 0) {
-#pragma unroll
-        for (int d = 1; d < 19; d++) nb[d] = adj_index_fast(reci, d, lane, P.nAct);
-    } else {  // warp-uniform and rare
-        const int *__restrict__ row = P.adjfull + (size_t)rec[0].y * 32 + lane;
-#pragma unroll
-        for (int d = 1; d < 19; d++) {
-            int cq = adj_index(rec[1 + 2 * (d - 1)], rec[2 + 2 * (d - 1)], lane, P.nAct);
-            if ((irr >> (d - 1)) & 1u) cq = __ldg(row + 32 * __popc(irr & ((1u << (d - 1)) - 1u)));
-            nb[d] = cq;
-        }
-    }
-}
-
 // One node: gather the incoming populations, collide, scatter.  n = active index (sparse layout), c = dense cell,
 // wst = this warp's quiet stamp (Dev::wstamp), rec = this warp's adjacency records in shared memory (sparse odd step).
-template <bool MP, bool ODD, bool SPARSE, bool PF>
+template <bool MP, bool ODD, bool SPARSE, int PF>
 __device__ __forceinline__ void node_update(const Dev &P, const int n, const int c, const int wst, const uint4 *rec) {
     double a[19], b[19];
     int nb[19];  // sparse odd step: active index of x+e_q
@@ -110,13 +92,13 @@ __device__ __forceinline__ void node_update(const Dev &P, const int n, const int
                     if (MP) b[OPC(d)] = ldpop(&P.gg[OPC(d)][cq]);
                     // software prefetch into L2 for the warps pf_dist nodes ahead: their neighbour indices differ from
                     // ours by ~pf_dist (same offsets), one request per 128-byte line
-                    if (PF && (lane & 15) == 0) {
+                    if (PF == 1 && (lane & 15) == 0) {
                         const int pq = min(cq + P.pf_dist, P.nAct - 1);
                         prefetch_l2(P.f[OPC(d)] + pq);
                         if (MP) prefetch_l2(P.gg[OPC(d)] + pq);
                     }
                 }
-                if (PF) {
+                if (PF == 1) {
                     const int wn = min((n + P.pf_dist) >> 5, (P.nA - 1) >> 5);
                     if (lane < 5) prefetch_l2(reinterpret_cast<const char *>(P.adj + (size_t)wn * MFLBM_ADJ_REC) + 128 * lane);
                     if (lane == 5) prefetch_l2(P.cellA + min(n + P.pf_dist, P.nA - 1));
@@ -179,10 +161,18 @@ __device__ __forceinline__ void node_update(const Dev &P, const int n, const int
     }
 }
 
-template <bool MP, bool ODD, bool SPARSE, bool PF = false>
-__global__ void __launch_bounds__(128, MP ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) k_collide(const Dev P, int k0, int n0, int n1) {
+// Threads per block of the collision kernel.  A block's registers are released when its LAST warp exits, so smaller
+// blocks leave fewer idle warp slots behind early finishers; measured (r01_v6): singlephase C2 +3 % with one warp per
+// block, multiphase C3 -1.6 % (more blocks to launch per byte moved) -> 32 for the singlephase kernels, 128 otherwise.
+__host__ __device__ constexpr int collide_block(bool mp) { return mp ? 128 : 32; }
+__host__ __device__ constexpr int collide_resident(bool mp) { return (mp ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) * 128 / collide_block(mp); }
+
+// PF: L2 software prefetch of the sparse odd step (populations, adjacency records and cell list of the warps pf_dist
+// nodes ahead)
+template <bool MP, bool ODD, bool SPARSE, int PF = 0>
+__global__ void __launch_bounds__(collide_block(MP), collide_resident(MP)) k_collide(const Dev P, int k0, int n0, int n1) {
     int c, n = 0, wst = 0;
-    __shared__ uint4 s_adj[SPARSE && ODD ? 4 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
+    __shared__ uint4 s_adj[SPARSE && ODD ? collide_block(MP) / 32 : 1][SPARSE && ODD ? MFLBM_ADJ_REC : 1];
     if (SPARSE) {
         // n0 is rounded down to a multiple of 32 by the launcher so that lane == n & 31 (the adjacency is per warp of
         // 32 consecutive A nodes)
@@ -213,173 +203,27 @@ __global__ void __launch_bounds__(128, MP ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) k
     node_update<MP, ODD, SPARSE, PF>(P, n, c, wst, SPARSE && ODD ? s_adj[threadIdx.x >> 5] : nullptr);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Pipelined, persistent flavour of the sparse kernels (Dev::pipe: 1 = odd step, 2 = odd and even steps).  The register file caps the collision kernel at 16 warps
-// per SM, and a warp that gathers its 38 populations into registers has nothing in flight while it collides and
-// scatters.  Here every warp owns a shared-memory stage of 38 x 32 doubles: while batch i is collided out of registers,
-// the populations of batch i+1 are already being gathered into the stage with cp.async (8-byte elements: neighbour runs
-// are not 16-byte aligned), and the adjacency records of batch i+2 into the other half of a double buffer.  The AA
-// pattern makes this legal: a node reads and writes the same 38 addresses and no two nodes share an address, so
-// reading batch i+1 before batch i is written back cannot observe batch i's results.  In-flight bytes per SM no longer
-// depend on the register allocation (16 warps x 9.7 KB).
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-#define MFLBM_ADJ_STAGE 40  // uint4 per adjacency buffer (37 used; keeps the buffers 128-byte granular)
-
-template <bool MP, bool ODD>
-__global__ void __launch_bounds__(128, MP ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS) k_collide_pipe(const Dev P, int n0, int n1) {
-    constexpr int NP = MP ? 38 : 19;
-    constexpr int WARP_BYTES = NP * 32 * 8 + (ODD ? 2 * MFLBM_ADJ_STAGE * 16 : 0);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char *wbase = smem_raw + (size_t)wib * WARP_BYTES;
-    const double *pop = reinterpret_cast<const double *>(wbase);
-    const uint4 *adjb = reinterpret_cast<const uint4 *>(wbase + NP * 32 * 8);
-    const unsigned pop_s = (unsigned)__cvta_generic_to_shared(wbase) + 8u * lane;
-    const unsigned adj_s = (unsigned)__cvta_generic_to_shared(wbase + NP * 32 * 8) + 16u * lane;
-    const int W = gridDim.x * 4;
-    const int wb1 = (n1 + 31) >> 5;
-    int wb = (n0 >> 5) + blockIdx.x * 4 + wib;
-    if (wb >= wb1) return;
-
-    auto fetch_adj = [&](int w, int buf) {  // one commit group, possibly empty
-        if (ODD && w < wb1) {
-            const uint4 *__restrict__ src = P.adj + (size_t)w * MFLBM_ADJ_REC;
-            const unsigned dst = adj_s + 16u * MFLBM_ADJ_STAGE * buf;
-            cp_async16(dst, src + lane);
-            if (lane < MFLBM_ADJ_REC - 32) cp_async16(dst + 16u * 32, src + 32 + lane);
-        }
-        cp_async_commit();
-    };
-    auto gather = [&](int w, int buf) {  // populations of batch w -> stage; one commit group, possibly empty
-        const int n = w * 32 + lane;
-        if (w < wb1 && n >= n0 && n < n1) {
-            if (ODD) {
-                int nb[19];
-                nb[0] = n;
-                decode_nb(P, adjb + MFLBM_ADJ_STAGE * buf, lane, nb);
-#pragma unroll
-                for (int d = 0; d < 19; d++) {
-                    cp_async8(pop_s + 256u * OPC(d), P.f[OPC(d)] + nb[d]);
-                    if (MP) cp_async8(pop_s + 256u * (19 + OPC(d)), P.gg[OPC(d)] + nb[d]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 19; q++) {
-                    cp_async8(pop_s + 256u * q, P.f[OPC(q)] + n);
-                    if (MP) cp_async8(pop_s + 256u * (19 + q), P.gg[OPC(q)] + n);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-
-    fetch_adj(wb, 0);
-    if (ODD) {
-        cp_async_wait<0>();
-        __syncwarp();
-    }
-    gather(wb, 0);
-    fetch_adj(wb + W, 1);
-    for (int buf = 0; wb < wb1; wb += W, buf ^= 1) {
-        const int n = wb * 32 + lane;
-        const bool valid = n >= n0 && n < n1;
-        int c = 0, wst = 0;
-        if (valid) {
-            c = P.cellA[n];
-            if (MP && P.use_tiles) wst = P.wstamp[wb];
-        }
-        cp_async_wait<1>();  // everything but the newest group (the adjacency fetch): this batch's populations are in
-        __syncwarp();
-        double a[19], b[19];
-        int nb[19];
-        if (valid) {
-#pragma unroll
-            for (int q = 0; q < 19; q++) {
-                a[q] = pop[q * 32 + lane];
-                if (MP) b[q] = pop[(19 + q) * 32 + lane];
-            }
-            if (ODD) {
-                nb[0] = n;
-                decode_nb(P, adjb + MFLBM_ADJ_STAGE * buf, lane, nb);
-            }
-        }
-        if (ODD) cp_async_wait<0>();  // adjacency of the next batch (issued one iteration ago)
-        __syncwarp();                 // stage and adjacency buffer `buf` are consumed by every lane
-        gather(wb + W, buf ^ 1);
-        fetch_adj(wb + 2 * W, buf);
-        if (valid) {
-            collide_node<MP, true>(P, c, wst, a, b);
-            if (ODD) {  // push q into slot opc(q) of x + e_q
-#pragma unroll
-                for (int q = 0; q < 19; q++) {
-                    stpop(&P.f[OPC(q)][nb[q]], a[q]);
-                    if (MP) stpop(&P.gg[OPC(q)][nb[q]], b[q]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 19; q++) {
-                    stpop(&P.f[q][n], a[q]);
-                    if (MP) stpop(&P.gg[q][n], b[q]);
-                }
-            }
-        }
-    }
-}
-
-template <bool MP, bool ODD>
-static void launch_pipe(const Dev &P, cudaStream_t st, int resident, int n0, int n1) {
-    constexpr int bytes = 4 * ((MP ? 38 : 19) * 32 * 8 + (ODD ? 2 * MFLBM_ADJ_STAGE * 16 : 0));
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_collide_pipe<MP, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        cudaFuncSetAttribute(k_collide_pipe<MP, ODD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
-    k_collide_pipe<MP, ODD><<<resident, 128, bytes, st>>>(P, n0, n1);
-}
-
 template <bool SPARSE>
 static void launch_collide_t(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1) {
     const Dev &P = c->d;
-    dim3 block(128), grid;
+    const int blk = collide_block(P.multiphase != 0);
+    dim3 block(blk), grid;
     int n0 = 0, n1 = 0;
     if (SPARSE) {
         n0 = c->kstartA[k0];
         n1 = c->kstartA[k1 + 1];
         if (n1 <= n0) return;
-        grid = dim3((n1 - (n0 & ~31) + 127) / 128);
-        const int resident = P.pipe_grid > 0 ? P.pipe_grid : 148 * (P.multiphase ? MFLBM_MP_BLOCKS : MFLBM_SP_BLOCKS);
-        if (P.pipe && (odd || P.pipe >= 2) && (int)grid.x > resident) {
-            if (P.multiphase) {
-                if (odd) launch_pipe<true, true>(P, st, resident, n0, n1);
-                else launch_pipe<true, false>(P, st, resident, n0, n1);
-            } else {
-                if (odd) launch_pipe<false, true>(P, st, resident, n0, n1);
-                else launch_pipe<false, false>(P, st, resident, n0, n1);
-            }
-            c->launches++;
-            return;
-        }
+        grid = dim3((n1 - (n0 & ~31) + blk - 1) / blk);
     } else {
-        grid = dim3((P.g.nx + 127) / 128, P.g.ny, k1 - k0 + 1);
+        grid = dim3((P.g.nx + blk - 1) / blk, P.g.ny, k1 - k0 + 1);
     }
     const bool pf = SPARSE && odd && P.pf_dist > 0;  // L2 software prefetch: a separate instantiation, no dead issue slots
     if (P.multiphase) {
-        if (pf) k_collide<true, true, SPARSE, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        if (pf) k_collide<true, true, SPARSE, SPARSE ? 1 : 0><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else if (odd) k_collide<true, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else k_collide<true, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     } else {
-        if (pf) k_collide<false, true, SPARSE, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        if (pf) k_collide<false, true, SPARSE, SPARSE ? 1 : 0><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else if (odd) k_collide<false, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else k_collide<false, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     }

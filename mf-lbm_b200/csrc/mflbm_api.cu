@@ -379,6 +379,8 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
         const unsigned jy = r2 / (unsigned)g.sx, ix = r2 - jy * (unsigned)g.sx;
         return idx[B((int)ix - 3 + EX(q), (int)jy - 3 + EY(q), (int)kz - 3 + EZ(q))];
     };
+    const bool stats = getenv("MFLBM_ADJ_STATS") != nullptr;  // developer: histogram of index runs per (warp, direction)
+    long long hist[16] = {0};
     std::vector<int> lcnt((size_t)nW * 18 + 18, 0);
     std::vector<long long> irr((size_t)nW + 1, 0);  // irregular rows per warp -> exclusive prefix
     std::vector<unsigned> irrmask((size_t)nW + 1, 0);
@@ -395,10 +397,19 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
                 prev = v;
             }
             lcnt[(size_t)w * 18 + (q - 1)] = links;
+            if (stats) {
+#pragma omp atomic
+                hist[jumps > 15 ? 15 : jumps]++;
+            }
             if (jumps > 5) im |= 1u << (q - 1);
         }
         irrmask[w] = im;
         irr[w] = __builtin_popcount(im);
+    }
+    if (stats) {
+        fprintf(stderr, "adjacency runs per (warp, direction):");
+        for (int j = 0; j < 16; j++) fprintf(stderr, " %d:%.3f%%", j, 100.0 * hist[j] / (18.0 * std::max(nW, 1)));
+        fprintf(stderr, "\n");
     }
     // exclusive prefix sums over the warps
     long long lsum[18] = {0};
@@ -543,10 +554,6 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
         // more than the L2 hits return), so it is off there.  MFLBM_PF_DIST overrides.
         const char *e = getenv("MFLBM_PF_DIST");
         d.pf_dist = e ? atoi(e) : (d.multiphase ? 0 : 65536);
-        e = getenv("MFLBM_PIPE");
-        d.pipe = e ? atoi(e) : 0;
-        e = getenv("MFLBM_PIPE_GRID");
-        d.pipe_grid = e ? atoi(e) : 0;
     }
     if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.adj, adj.size(), false) ||
         dev_alloc(ctx, &d.adjfull, full.size(), false) || dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))
@@ -1029,8 +1036,7 @@ extern "C" int mflbm_cal_saturation(mflbm_ctx *ctx, double *v1, double *v2) {
     if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
     CU(cudaSetDevice(ctx->device));
     const int nz = ctx->cfg.nz;
-    launch_saturation(ctx, ctx->s_main, ctx->red_dev);
-    const int np = nz * MFLBM_SAT_SEG;
+    const int np = launch_saturation(ctx, ctx->s_main, ctx->red_dev);
     if (check_launch(ctx) || fetch_red(ctx, 2 * np)) return MFLBM_ERR_CUDA;
     double a = 0, b = 0;
     for (int k = 0; k < np; k++) { a += ctx->red_host[k]; b += ctx->red_host[np + k]; }
@@ -1169,7 +1175,8 @@ extern "C" long long mflbm_device_bytes(const mflbm_ctx *ctx) { return ctx ? ctx
 
 // Internal (not part of include/mflbm.h): host-only self-test of the node numbering + compressed adjacency, callable
 // without a GPU (tests/test_adjacency.py).  Returns 0 when every (node, direction) decodes to the direct lookup and the
-// link slots of each direction are a permutation-free ranking; fills counts[0..3] = nA, nAct, total links, irregular rows.
+// link slots of each direction are a permutation-free ranking; fills counts[0..4] = nA, nAct, total links, irregular rows,
+// warps with at least one irregular row (counts must hold 8 values).
 extern "C" int mflbmx_adjacency_selftest(int nx, int ny, int nz, const int8_t *walls, long long *counts) {
     Grid g;
     g.nx = nx; g.ny = ny; g.nz = nz;
@@ -1203,6 +1210,9 @@ extern "C" int mflbmx_adjacency_selftest(int nx, int ny, int nz, const int8_t *w
         long long links = 0;
         for (int q = 1; q < 19; q++) links += H.nlink[q];
         counts[0] = H.nA; counts[1] = H.nAct; counts[2] = links; counts[3] = (long long)H.adjfull.size() / 32;
+        long long iw = 0;
+        for (int w = 0; w < (H.nA + 31) / 32; w++) iw += H.adj[(size_t)w * MFLBM_ADJ_REC].x != 0;
+        counts[4] = iw;
     }
     return MFLBM_OK;
 }

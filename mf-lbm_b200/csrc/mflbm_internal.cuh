@@ -123,8 +123,6 @@ struct Dev {
     uint4 *adj;       // [ceil(nA/32)][37]
     int *adjfull;     // [rows][32]
     int pf_dist;      // L2 software-prefetch distance of the odd step in nodes (0 = off)
-    int pipe;         // 0: one block per 128 nodes; 1: pipelined persistent kernel on odd steps; 2: on odd and even steps
-    int pipe_grid;    // blocks of the pipelined kernels (0: one wave of resident blocks); tests shrink it
     int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
@@ -258,7 +256,7 @@ void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
 void launch_macro(mflbm_ctx *c, cudaStream_t st);
 void launch_monitor(mflbm_ctx *c, cudaStream_t st, double *out /*device, (10)*nz*/);
-void launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out /*device, 2*nz*/);
+int launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out /*device, 2 rows of partial sums*/);
 void launch_breakthrough(mflbm_ctx *c, cudaStream_t st, double *out);
 void launch_steady_phasefield(mflbm_ctx *c, cudaStream_t st, double *out /*2*nz*/);
 void launch_steady_cappres(mflbm_ctx *c, cudaStream_t st, double *out /*5*nz*/);

@@ -15,13 +15,13 @@ def _selftest(walls):
     M.build()
     lib = M.load()
     fn = lib.mflbmx_adjacency_selftest
-    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong * 4)]
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong * 8)]
     w = np.asfortranarray(walls, dtype=np.int8)
     nx, ny, nz = (s - 4 for s in w.shape)
-    counts = (C.c_longlong * 4)()
+    counts = (C.c_longlong * 8)()
     rc = fn(nx, ny, nz, w.ctypes.data, C.byref(counts))
     assert rc == 0, lib.mflbm_last_error(None).decode()
-    return list(counts)
+    return list(counts)[:4]
 
 
 def _with_ghosts(core, wall_xy=True):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: parity tests, then a sweep of kernel tunings (library variants + environment knobs), then ncu captures.
 # usage: tools/sweep.sh TAG
-TAG=${1:-r01_v4}
+TAG=${1:-r01_v6}
 O=gpurun_out
 mkdir -p $O
 L=$O/${TAG}_sweep.log
@@ -23,25 +23,18 @@ counters() {  # label, workload, env...: DRAM / L2 counters of one odd + one eve
     --clock-control none -k regex:k_collide -s 4 -c 2 --csv --log-file $O/${TAG}_ctr_${label}_${wl}.csv python bench.py --workload $wl --steps 2 --warmup 4 --no-cpu-baseline --no-e2e > $O/${TAG}_ctr_${label}_${wl}.log 2>&1
 }
 timeout 1200 python -m pytest tests -m gpu -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $O/${TAG}_pytest.log
-tail -5 $O/${TAG}_pytest.log
-MFLBM_PIPE=2 MFLBM_PIPE_GRID=24 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_spherepack_gpu.py -q > $O/${TAG}_pytest_pipe.log 2>&1; echo "pytest exit $?" >> $O/${TAG}_pytest_pipe.log
-tail -5 $O/${TAG}_pytest_pipe.log
+tail -n 5 $O/${TAG}_pytest.log
 run base c3 A=1
+run static_bc_tiles c3 MFLBM_STATIC_BC_TILES=1
+run pf2 c3 MFLBM_PF_DIST=65536 MFLBM_PF_MODE=2
+run pf2_32k c3 MFLBM_PF_DIST=32768 MFLBM_PF_MODE=2
+run blk64 c3 MFLBM_LIB_VARIANT=blk64
+run blk32 c3 MFLBM_LIB_VARIANT=blk32
+run blk64_pf2 c3 MFLBM_LIB_VARIANT=blk64 MFLBM_PF_DIST=65536 MFLBM_PF_MODE=2
 run base c2 A=1
-run pipe1 c3 MFLBM_PIPE=1
-run pipe2 c3 MFLBM_PIPE=2
-run pipe1 c2 MFLBM_PIPE=1
-run pipe2 c2 MFLBM_PIPE=2
-run pipe1_pf0 c2 MFLBM_PIPE=1 MFLBM_PF_DIST=0
-run skew4352 c3 MFLBM_ARRAY_SKEW=4352
-run skew69888 c3 MFLBM_ARRAY_SKEW=69888
-run skew4352_pipe1 c3 MFLBM_ARRAY_SKEW=4352 MFLBM_PIPE=1
-run skew4352 c2 MFLBM_ARRAY_SKEW=4352
+run pf2 c2 MFLBM_PF_MODE=2
+run blk64 c2 MFLBM_LIB_VARIANT=blk64
+run blk32 c2 MFLBM_LIB_VARIANT=blk32
 cat $L
-counters base c3 A=1
-counters skew c3 MFLBM_ARRAY_SKEW=4352
-counters pipe1 c3 MFLBM_PIPE=1
-counters base c2 A=1
-counters pipe1 c2 MFLBM_PIPE=1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_collide_pipe -s 2 -c 1 -f -o $O/${TAG}_pipe_c3 env MFLBM_PIPE=1 python bench.py --steps 2 --warmup 4 --no-cpu-baseline --no-e2e > $O/${TAG}_ncufull_pipe_c3.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_c3.csv python bench.py --steps 4 --warmup 6 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_c3.log 2>&1
 ls -la $O

@@ -181,6 +181,10 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the (untimed) host-side setup -- geometry, node lists, adjacency -- is OpenMP
+        # code in libmflbm.so / libmflbm_host.so, loaded below: give every rank its share of the host cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = world if world > 1 else 1
     spec = workload_spec(args.workload, n_gpus)

@@ -160,6 +160,32 @@ long long mflbm_device_bytes(const mflbm_ctx *ctx);
  * torch.distributed in bench.py); replaces MPI_CART_CREATE for the z ring (MP/Mpi_misc.F90:19-38) */
 int mflbm_nccl_unique_id(unsigned char id[128]);
 
+/* ---- geometry preprocessing on the device -------------------------------------------------
+ * Replaces geometry_preprocessing_new (MP/Geometry_preprocessing.F90:9-512), called from set_walls / the main
+ * program before initialization (MP/Main_multiphase.F90:98): classification of the wall array into solid / fluid
+ * boundary nodes, the two node lists of the colour-gradient chain (types above) with neighbour lists, la_weight and the
+ * ISO8 wall normals of the four-times smoothed wall field.  The reference does this serially on rank 0 over the whole
+ * lattice and broadcasts global lists (:4-8 flags it as too slow for large domains); here every rank hands in the z
+ * window of the global wall array around its slab and gets its LOCAL lists (:424-507) back, in the reference's order
+ * (k outer, i inner) with local iz.  No context is needed; lists are malloc'ed by the library. */
+typedef struct {
+    int32_t struct_size;              /* sizeof(mflbm_geometry_config) */
+    int32_t nxGlobal, nyGlobal, nzGlobal;
+    int32_t wk0, wk1;                 /* global planes (1-based, inclusive) held in walls_window(1:nxG,1:nyG,wk0:wk1); the window
+                                         must reach the lattice end or extend >= 10 planes beyond the slab on that side */
+    int32_t idz, npz;                 /* slab of this rank: planes idz*nz+1 .. idz*nz+nz, nz = nzGlobal/npz */
+    int32_t iper, jper, kper;         /* periodic_indicator (wrap instead of replicate in the ghost layers, :56-108) */
+    int32_t device;                   /* CUDA device ordinal, -1 = current */
+    double theta;                     /* contact angle stored in every fluid node, radians, already converted
+                                         (pi - theta, MP/IO_multiphase.F90:467-468) */
+} mflbm_geometry_config;
+
+int mflbm_geometry_preprocess(const mflbm_geometry_config *cfg, const int8_t *walls_window, mflbm_solid_node **solid,
+                              int32_t *num_solid, mflbm_fluid_node **fluid, int32_t *num_fluid,
+                              int64_t *num_solid_scanned, int64_t *num_fluid_scanned);
+void mflbm_geometry_free(void *list);
+const char *mflbm_geometry_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

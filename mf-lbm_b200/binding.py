@@ -49,7 +49,12 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
            "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
-           "mflbm_tile_stats")
+           "mflbm_tile_stats", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error")
+
+
+class GeometryConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("struct_size", "nxGlobal", "nyGlobal", "nzGlobal", "wk0", "wk1", "idz", "npz", "iper", "jper",
+                                         "kper", "device")] + [("theta", C.c_double)]
 
 
 class MflbmError(RuntimeError):
@@ -109,8 +114,41 @@ def load(strict=False):
     lib.mflbm_device_bytes.argtypes = [vp]
     lib.mflbm_device_bytes.restype = C.c_longlong
     lib.mflbm_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte * 128)]
+    lib.mflbm_geometry_preprocess.argtypes = [C.POINTER(GeometryConfig), C.c_void_p, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.mflbm_geometry_free.argtypes = [vp]
+    lib.mflbm_geometry_free.restype = None
+    lib.mflbm_geometry_last_error.restype = C.c_char_p
     _LIBS[key] = lib
     return lib
+
+
+def geometry_preprocess(walls_window, nzGlobal=None, wk0=1, idz=0, npz=1, periodic=(0, 0, 0), theta=0.0, device=-1, strict=False):
+    """geometry_preprocessing_new (MP/Geometry_preprocessing.F90:9-512) on the device through the C ABI.
+
+    walls_window: int8 (nxGlobal, nyGlobal, planes) = global planes wk0 .. wk0+planes-1 of the wall array.  Returns
+    (solid_nodes, fluid_nodes, num_solid_scanned, num_fluid_scanned) with the node lists as numpy record arrays of the
+    reference's derived types (SOLID_DTYPE / FLUID_DTYPE), local to slab idz of npz."""
+    lib = load(strict)
+    w = np.asfortranarray(walls_window, dtype=np.int8)
+    nx, ny, planes = w.shape
+    cfg = GeometryConfig(struct_size=C.sizeof(GeometryConfig), nxGlobal=nx, nyGlobal=ny, nzGlobal=nzGlobal or planes, wk0=wk0,
+                         wk1=wk0 + planes - 1, idz=idz, npz=npz, iper=periodic[0], jper=periodic[1], kper=periodic[2], device=device,
+                         theta=theta)
+    ps, pf = C.c_void_p(), C.c_void_p()
+    ns, nf = C.c_int32(), C.c_int32()
+    gs, gf = C.c_int64(), C.c_int64()
+    rc = lib.mflbm_geometry_preprocess(C.byref(cfg), w.ctypes.data, C.byref(ps), C.byref(ns), C.byref(pf), C.byref(nf), C.byref(gs),
+                                       C.byref(gf))
+    if rc:
+        raise MflbmError("mflbm_geometry_preprocess: %s" % lib.mflbm_geometry_last_error().decode())
+    try:
+        solid = np.frombuffer((C.c_char * (96 * ns.value)).from_address(ps.value), dtype=SOLID_DTYPE).copy() if ns.value else np.zeros(0, SOLID_DTYPE)
+        fluid = np.frombuffer((C.c_char * (48 * nf.value)).from_address(pf.value), dtype=FLUID_DTYPE).copy() if nf.value else np.zeros(0, FLUID_DTYPE)
+    finally:
+        lib.mflbm_geometry_free(ps)
+        lib.mflbm_geometry_free(pf)
+    return solid, fluid, gs.value, gf.value
 
 
 def nccl_unique_id():

@@ -51,6 +51,15 @@ def workload_spec(name, n_gpus):
                                  excluded_layers="10,10"),
                     label="multiphase_3D scCO2/brine drainage, synthetic random-sphere-pack %dx%dx%d (porosity 0.36, "
                           "10 buffer layers each end), velocity inlet / convective outlet" % (n, n, n * n_gpus))
+    if name == "c5":  # configs[4]: one 1536x1536x192 slab per GPU (N = 8 is the 1536^3 weak-scaling target), same physics as C3
+        return dict(multiphase=True, nx=1536, ny=1536, nz=192 * n_gpus, periodic=False,
+                    geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=3, buffer=10),
+                    control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
+                                 RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
+                                 initial_interface_position=8.0, initial_fluid_distribution_option=1,
+                                 excluded_layers="10,10"),
+                    label="multiphase_3D weak-scaling slab 1536x1536x%d (%d x 192 planes, sphere pack porosity 0.36, 10 buffer "
+                          "layers at the lattice ends), velocity inlet / convective outlet" % (192 * n_gpus, n_gpus))
     if name == "c2":  # configs[1]
         n = int(os.environ.get("MFLBM_BENCH_N", "240"))
         return dict(multiphase=False, nx=n, ny=n, nz=(n + 20) * n_gpus, periodic=True,

@@ -63,7 +63,32 @@ module mflbm_c
         type(c_ptr) :: solid_boundary_nodes, fluid_boundary_nodes
     end type mflbm_arrays
 
+    ! struct mflbm_geometry_config (device geometry preprocessing, SURVEY 8(f) item 1)
+    type, bind(c) :: mflbm_geometry_config
+        integer(c_int32_t) :: struct_size
+        integer(c_int32_t) :: nxGlobal, nyGlobal, nzGlobal
+        integer(c_int32_t) :: wk0, wk1
+        integer(c_int32_t) :: idz, npz
+        integer(c_int32_t) :: iper, jper, kper
+        integer(c_int32_t) :: device
+        real(c_double) :: theta
+    end type mflbm_geometry_config
+
     interface
+        integer(c_int) function mflbm_geometry_preprocess(cfg, walls_window, solid, num_solid, fluid, num_fluid, &
+                                                          num_solid_scanned, num_fluid_scanned) &
+            bind(c, name="mflbm_geometry_preprocess")
+            import :: c_int, c_ptr, c_int32_t, c_int64_t, mflbm_geometry_config
+            type(mflbm_geometry_config), intent(in) :: cfg
+            type(c_ptr), value :: walls_window              ! c_loc(walls_global(1,1,wk0)), integer(kind=1)
+            type(c_ptr), intent(out) :: solid, fluid        ! malloc'ed lists, release with mflbm_geometry_free
+            integer(c_int32_t), intent(out) :: num_solid, num_fluid
+            integer(c_int64_t), intent(out) :: num_solid_scanned, num_fluid_scanned
+        end function
+        subroutine mflbm_geometry_free(list) bind(c, name="mflbm_geometry_free")
+            import :: c_ptr
+            type(c_ptr), value :: list
+        end subroutine
         integer(c_int) function mflbm_create(cfg, ctx) bind(c, name="mflbm_create")
             import :: c_int, c_ptr, mflbm_config
             type(mflbm_config), intent(in) :: cfg
@@ -352,3 +377,41 @@ subroutine monitor_breakthrough_device_part(outlet_phase1_sum)
     call mflbm_check(mflbm_monitor_breakthrough(mflbm_handle, cnt), 'mflbm_monitor_breakthrough')
     outlet_phase1_sum = cnt
 end subroutine monitor_breakthrough_device_part
+
+! geometry_preprocessing_new (MP/Geometry_preprocessing.F90:9-512), called from MP/Main_multiphase.F90:98 on every rank
+! (the reference does the work on rank 0 and broadcasts): the body below replaces it.  Each rank hands the library the
+! planes of walls_global around its slab and receives its LOCAL lists, which it copies into the allocatable module
+! arrays solid_boundary_nodes / fluid_boundary_nodes (MP/Module.F90:96,104) exactly as :424-507 does.
+subroutine geometry_preprocessing_new
+    use, intrinsic :: iso_c_binding
+    use mflbm_c
+    use mflbm_glue
+    use Misc_module
+    use Fluid_multiphase
+    use mpi_variable
+    implicit none
+    type(mflbm_geometry_config) :: gc
+    type(c_ptr) :: ps, pf
+    type(indirect_solid_boundary_nodes), pointer :: s(:)
+    type(indirect_fluid_boundary_nodes), pointer :: f(:)
+    integer(c_int32_t) :: ns, nf
+    integer(c_int64_t) :: gs, gf
+    gc%struct_size = int(c_sizeof(gc), c_int32_t)
+    gc%nxGlobal = nxGlobal; gc%nyGlobal = nyGlobal; gc%nzGlobal = nzGlobal
+    gc%wk0 = max(1, idz*nz + 1 - 12); gc%wk1 = min(nzGlobal, idz*nz + nz + 12)
+    gc%idz = idz; gc%npz = npz
+    gc%iper = iper; gc%jper = jper; gc%kper = kper
+    gc%device = -1
+    gc%theta = theta
+    call mflbm_check(mflbm_geometry_preprocess(gc, c_loc(walls_global(1, 1, gc%wk0)), ps, ns, pf, nf, gs, gf), &
+                     "mflbm_geometry_preprocess")
+    num_solid_boundary = ns; num_fluid_boundary = nf
+    num_solid_boundary_global = int(gs); num_fluid_boundary_global = int(gf)
+    call c_f_pointer(ps, s, [max(ns, 1)]); call c_f_pointer(pf, f, [max(nf, 1)])
+    if (allocated(solid_boundary_nodes)) deallocate(solid_boundary_nodes)
+    if (allocated(fluid_boundary_nodes)) deallocate(fluid_boundary_nodes)
+    allocate(solid_boundary_nodes(max(ns, 1)), fluid_boundary_nodes(max(nf, 1)))
+    if (ns > 0) solid_boundary_nodes(1:ns) = s(1:ns)
+    if (nf > 0) fluid_boundary_nodes(1:nf) = f(1:nf)
+    call mflbm_geometry_free(ps); call mflbm_geometry_free(pf)
+end subroutine geometry_preprocessing_new

@@ -27,6 +27,7 @@ __device__ __forceinline__ void phi_inlet_ghost(const Dev &P, int i, int j, int 
     P.phi[c0 - P.g.sxy] = v;
     P.phi[c0 - 2 * P.g.sxy] = v;
     P.phi[c0 - 3 * P.g.sxy] = v;
+    if (P.bc_lo_dyn && P.use_tiles) tile_record(P, c0, v);  // k = 0..-3 share one tile layer (kz = 3..0)
 }
 
 template <bool MP, bool AFTER>
@@ -122,6 +123,10 @@ __global__ void k_outlet_convective(const Dev P) {
         P.phi[cp + sxy] = v;
         P.phi[cp + 2 * sxy] = v;
         P.phi[cp + 3 * sxy] = v;
+        if (P.bc_hi_dyn && P.use_tiles) {  // k = nz+1 .. nz+4 lie in one or two tile layers
+            tile_record(P, cp, v);
+            if (nz & 3) tile_record(P, cp + 3 * sxy, v);
+        }
     }
     if (P.sparse && wi) return;
 #pragma unroll
@@ -160,6 +165,10 @@ __global__ void k_outlet_pressure(const Dev P) {
     if (MP) {
         phin = P.phi[cn];
         P.phi[cp] = phin; P.phi[cp + sxy] = phin; P.phi[cp + 2 * sxy] = phin; P.phi[cp + 3 * sxy] = phin;
+        if (P.bc_hi_dyn && P.use_tiles) {
+            tile_record(P, cp, phin);
+            if (nz & 3) tile_record(P, cp + 3 * sxy, phin);
+        }
     }
     if (P.sparse && wi) return;
     double *const *F = P.f;

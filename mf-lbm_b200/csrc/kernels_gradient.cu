@@ -197,10 +197,14 @@ __global__ void __launch_bounds__(128) k_tile_static(const Dev P, const unsigned
     const int c = P.g.cell(i, j, k);
     const int t = P.g.tile_of(c, P.ntx, P.nty);
     if (k <= 0 || k >= nz + 1) {
-        // Measured alternative (r01_v6): letting the inlet / outlet kernels record the class of the phi they write makes
-        // the end tiles quiet too, +0.7 % MLUPS on C3, but the long-run parity test lost bit-exactness -> not kept.
-        tile_or(P.tstat, t, TILE_X);
-        return;
+        // ghost planes filled by the periodic wrap / the halo exchange: always X.  Ghost planes rewritten every step by
+        // an inlet / outlet kernel (columns 1..nx x 1..ny): that kernel records the class of what it writes
+        // (tile_record); the cells beside those columns are constant and classified below like any other unlisted cell.
+        if (!(k <= 0 ? P.bc_lo_dyn : P.bc_hi_dyn)) {
+            tile_or(P.tstat, t, TILE_X);
+            return;
+        }
+        if (i >= 1 && i <= nx && j >= 1 && j <= ny) return;
     }
     const int a = P.smap[c];
     if (a >= 0 && a < P.nA) return;  // fluid node: dynamic class
@@ -265,13 +269,59 @@ __global__ void k_tile_update(const Dev P, int cur, int stamp) {
 // knows |grad phi| = 0 there without reading anything (see Dev::wstamp).
 __device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int stamp) {
     const int tx = tile % P.ntx, ty = (tile / P.ntx) % P.nty, tz = tile / (P.ntx * P.nty);
-#pragma unroll
-    for (int m = 0; m < 2; m++) {
-        const int e = threadIdx.x + 64 * m;  // cell of the 8x4x4 tile
+    for (int e = threadIdx.x; e < 128; e += blockDim.x) {  // cell of the 8x4x4 tile
         const int ix = 8 * tx + (e & 7), jy = 4 * ty + ((e >> 3) & 3), kz = 4 * tz + (e >> 5);
         if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
         const int a = P.smap[P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz];
         if (a >= 0 && a < P.nA) P.wstamp[a >> 5] = stamp;
+    }
+}
+
+// K4 on the active tiles with phi staged through shared memory: the 128 threads of a block own the 128 cells of one
+// 8x4x4 tile; the tile's phi box with a one-cell halo (10 x 6 x 6 values, rows of 10 contiguous doubles) is loaded once,
+// cooperatively, and the 18-neighbour ISO4 stencils of all cells read it from there -- 360 loads per tile instead of
+// 19 gathers per non-solid cell.  Cells are enumerated geometrically (non-solid cells of the (-1:n+2)^3 box, the
+// reference's loop range, MP/Phase_gradient.F90:36-38), so neither the cell list nor its per-tile CSR is read.
+// Same expressions in the same order as gradient_at (ddx / ddy / ddz), hence the same bits (parity suite green with it).
+// MEASURED (r01_v11, profiles/r01_v11_k4.txt): slower than the list gathers of k_chain_tiles<4> -- 1050 vs 775 us on the
+// 1536x1536x192 slab, 8600 vs 8620 MLUPS on C3: only ~36 % of a tile's cells are pore space, the list version packs
+// them into full warps and its 19 gathers hit L1, while this one pays 360 + 128 loads and two barriers per tile
+// whatever the porosity.  Kept selectable (MFLBM_K4_SMEM=1) as the evidence; the list version is the default.
+#define MFLBM_K4_ROW 24  // shared-memory row pitch in doubles (10 used): 8 mod 16 keeps half-warps conflict-free
+__global__ void __launch_bounds__(128) k_gradient_tiles(const Dev P, int stamp) {
+    __shared__ double sphi[6 * 6 * MFLBM_K4_ROW];
+    const int count = P.tcount[0];
+    const int sx = P.g.sx, sxy = P.g.sxy;
+    const int tid = threadIdx.x;
+    const int a = tid & 7, b = (tid >> 3) & 3, d = tid >> 5;
+    for (int t = blockIdx.x; t < count; t += gridDim.x) {
+        const int tile = P.tact[t];
+        const int tx = tile % P.ntx, ty = (tile / P.ntx) % P.nty, tz = tile / (P.ntx * P.nty);
+        const int ix0 = 8 * tx, jy0 = 4 * ty, kz0 = 4 * tz;  // padded coordinates (i+3, j+3, k+3) of the tile origin
+        if (stamp > 0) tile_stamp_warps(P, tile, stamp);
+        for (int e = tid; e < 360; e += 128) {
+            const int ha = e % 10, hb = (e / 10) % 6, hd = e / 60;
+            const long long c = (long long)(P.g.base - 4) + (ix0 + ha - 1) + (long long)sx * (jy0 + hb - 1) + (long long)sxy * (kz0 + hd - 1);
+            sphi[ha + MFLBM_K4_ROW * (hb + 6 * hd)] = (c >= 0 && c < P.g.ntot) ? P.phi[c] : 0.0;
+        }
+        __syncthreads();
+        const int ix = ix0 + a, jy = jy0 + b, kz = kz0 + d;  // this thread's cell
+        const bool inbox = ix >= 2 && ix <= P.g.nx + 5 && jy >= 2 && jy <= P.g.ny + 5 && kz >= 2 && kz <= P.g.nz + 5;
+        const int c = P.g.base - 4 + ix + sx * jy + sxy * kz;
+        if (inbox && P.walls[c] != 1) {
+            const double *__restrict__ sp = sphi + (a + 1) + MFLBM_K4_ROW * ((b + 1) + 6 * (d + 1));
+            auto v = [&](int da, int db, int dd) { return sp[da + MFLBM_K4_ROW * (db + 6 * dd)]; };
+            const double gx = ddx(v), gy = ddy(v), gz = ddz(v);
+            const double cn = sqrt(gx * gx + gy * gy + gz * gz);
+            if (cn < 1e-6) {
+                if (P.c_norm[c] != 0.0) {  // lazy: bulk nodes already hold zeros (see gradient_at)
+                    P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
+                }
+            } else {
+                P.cn_x[c] = gx / cn; P.cn_y[c] = gy / cn; P.cn_z[c] = gz / cn; P.c_norm[c] = cn;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -375,7 +425,10 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
         const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
         // K4 also stamps the warps of the active tiles (stepping only; nG > 0 whenever there is a fluid node)
         if (P.num_solid > 0) k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0);
-        if (P.nG > 0) k_chain_tiles<4><<<grid, 64, 0, st>>>(P, stepping ? c->tile_stamp : 0);
+        if (P.nG > 0) {
+            if (P.k4_smem) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, stepping ? c->tile_stamp : 0);
+            else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, stepping ? c->tile_stamp : 0);
+        }
         if (P.num_fluid > 0) k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0);
         if (P.num_solid > 0) k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0);
         c->launches += 1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0);

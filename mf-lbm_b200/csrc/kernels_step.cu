@@ -397,6 +397,35 @@ __global__ void k_halo_pack(const Dev P, double *buf_lo, double *buf_hi, int pus
     }
 }
 
+// phi classes of the ghost planes the halo exchange just filled (k = -3..0 from the z-1 neighbour, nz+1..nz+4 from the
+// z+1 neighbour), recorded like the collision kernel records the classes of the fluid nodes: without it the tiles along
+// a slab interface would have to count as "unknown" (X) for ever and their gradient chain could never be skipped.
+__global__ void __launch_bounds__(128) k_halo_phi_classes(const Dev P, int lo, int hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1;
+    if (i > P.g.nx) return;
+    const int nz = P.g.nz;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        if (lo) {
+            const int c = P.g.cell(i, j, -kk);
+            tile_record(P, c, P.phi[c]);
+        }
+        if (hi) {
+            const int c = P.g.cell(i, j, nz + 1 + kk);
+            tile_record(P, c, P.phi[c]);
+        }
+    }
+}
+
+void launch_halo_phi_classes(mflbm_ctx *c, cudaStream_t st, bool lo, bool hi) {
+    const Dev &P = c->d;
+    if (!P.multiphase || !P.use_tiles || (!lo && !hi)) return;
+    dim3 block(128), grid((P.g.nx + 127) / 128, P.g.ny);
+    k_halo_phi_classes<<<grid, block, 0, st>>>(P, lo ? 1 : 0, hi ? 1 : 0);
+    c->launches++;
+}
+
 void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack) {
     const Dev &P = c->d;
     dim3 block(128), grid((P.g.nx + 127) / 128, P.g.ny);

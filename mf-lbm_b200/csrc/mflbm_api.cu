@@ -232,6 +232,17 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     }();
     if (rc) CREATE_FAIL(rc);
     ctx->open_z = (cfg->kper == 0 && cfg->domain_wall_status_z_min == 0 && cfg->domain_wall_status_z_max == 0);
+    // which phi ghost faces are rewritten every step by a kernel that also records their phi classes: the inlet / outlet
+    // kernels (same conditions as launch_bc, kernels_bc.cu) or the halo exchange (same conditions as halo_exchange);
+    // the ghost planes of the single-GPU periodic wrap stay "unknown"
+    {
+        const bool dyn = getenv("MFLBM_STATIC_BC_TILES") == nullptr;
+        const bool halo = cfg->use_nccl && cfg->npz > 1;
+        ctx->d.bc_lo_dyn = dyn && ((ctx->open_z && cfg->idz == 0 && (cfg->inlet_BC == 1 || cfg->inlet_BC == 2)) ||
+                                   (halo && (cfg->kper == 1 || cfg->idz != 0)));
+        ctx->d.bc_hi_dyn = dyn && ((ctx->open_z && cfg->idz == cfg->npz - 1 && (cfg->outlet_BC == 1 || cfg->outlet_BC == 2)) ||
+                                   (halo && (cfg->kper == 1 || cfg->idz != cfg->npz - 1)));
+    }
     ctx->peer_lo = (cfg->idz - 1 + cfg->npz) % cfg->npz;
     ctx->peer_hi = (cfg->idz + 1) % cfg->npz;
     if (cfg->use_nccl && cfg->npz > 1) {
@@ -586,6 +597,7 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     d.sparse = variant == 2;
     d.full_curv = variant == 1;
     d.use_tiles = (d.sparse && d.multiphase && !getenv("MFLBM_NO_TILES")) ? 1 : 0;
+    d.k4_smem = getenv("MFLBM_K4_SMEM") ? 1 : 0;  // measured slower than the list gathers (kernels_gradient.cu), off by default
     if (d.use_tiles) {
         d.ntx = g.sx / 8;
         d.nty = (g.ny + 8 + 3) / 4;
@@ -893,6 +905,7 @@ static int halo_exchange(mflbm_ctx *ctx, cudaStream_t st, bool push) {
     }
     NC(ctx->nccl->GroupEnd());
     if (d.sparse) launch_halo_pack(ctx, st, has_lo ? ctx->halo_buf[2] : nullptr, has_hi ? ctx->halo_buf[3] : nullptr, push, true);
+    launch_halo_phi_classes(ctx, st, has_lo && d.bc_lo_dyn, has_hi && d.bc_hi_dyn);
     return 0;
 }
 

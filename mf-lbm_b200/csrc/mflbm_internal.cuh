@@ -134,6 +134,10 @@ struct Dev {
     // class for two consecutive steps is QUIET: every colour gradient there is below the reference's 1e-6 cut-off,
     // i.e. exactly zero, so the gradient chain K3..K6 and the c_norm read of the collision kernel are skipped.
     int use_tiles;
+    int k4_smem;               // 1: K4 on active tiles stages phi through shared memory (k_gradient_tiles)
+    int bc_lo_dyn, bc_hi_dyn;  // 1: the phi ghost planes below k=1 / above k=nz are rewritten every step by an inlet /
+                               // outlet kernel or by the halo exchange, and whoever writes them records their phi
+                               // classes like the collision kernel does (tile_record)
     int ntx, nty, ntz, ntiles;
     int tile_cur;            // which tcls / tU buffer the current step writes
     unsigned char *tcls[2];  // per-step class bits of the fluid nodes (atomicOr by k_collide)
@@ -156,6 +160,21 @@ struct Dev {
     double s_e, s_e2, s_q, s_nu, s_pi, s_t;
     double rk_weight2;  // 1/sqrt(2)/36 evaluated on the host like MP/Module.F90:225
 };
+
+#ifdef __CUDACC__
+// phi class of one cell into the class buffer of the current step (see Dev::tcls): P |phi-1|<=1e-7, M |phi+1|<=1e-7, X else
+__device__ __forceinline__ void tile_record(const Dev &P, int c, double phi) {
+    const int tile = P.g.tile_of(c, P.ntx, P.nty);
+    const unsigned bits = fabs(phi - 1.0) <= 1e-7 ? 1u : (fabs(phi + 1.0) <= 1e-7 ? 2u : 4u);
+    const unsigned key = ((unsigned)tile << 3) | bits;
+    // consecutive columns of a row mostly share (tile, class): the first lane of every run of equal keys reports
+    const unsigned act = __activemask();
+    const unsigned prev = __shfl_up_sync(act, key, 1);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != key)
+        atomicOr((unsigned *)(P.tcls[P.tile_cur] + (tile & ~3)), bits << (8 * (tile & 3)));
+}
+#endif
 
 #define MFLBM_ADJ_REC 37  // uint4 records per warp
 #define MFLBM_SAT_SEG 4   // blocks per z slice of k_saturation (2 * nz * MFLBM_SAT_SEG partial sums fit red_len)
@@ -247,6 +266,7 @@ void launch_collide(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, int k1);
 void launch_fill_smap(mflbm_ctx *c, cudaStream_t st);
 void launch_repack_sparse(mflbm_ctx *c, cudaStream_t st, double *pdf, double *packed, bool to_dev, int q);
 void launch_halo_pack(mflbm_ctx *c, cudaStream_t st, double *buf_lo, double *buf_hi, bool push, bool unpack);
+void launch_halo_phi_classes(mflbm_ctx *c, cudaStream_t st, bool lo, bool hi);
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping = false);
 void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st);
 void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);

@@ -498,6 +498,35 @@ void Driver::geometry_preprocessing_new() {  // MP/Geometry_preprocessing.F90:9-
     }
 }
 
+// the same through the C ABI: the device kernels classify, list and compute the wall normals of this slab's window
+bool Driver::geometry_preprocessing_device() {
+    mflbm_geometry_config gc;
+    memset(&gc, 0, sizeof(gc));
+    gc.struct_size = (int32_t)sizeof(gc);
+    gc.nxGlobal = c.nxGlobal; gc.nyGlobal = c.nyGlobal; gc.nzGlobal = c.nzGlobal;
+    gc.wk0 = wk0; gc.wk1 = wk1;
+    gc.idz = idz; gc.npz = c.npz;
+    gc.iper = c.iper; gc.jper = c.jper; gc.kper = c.kper;
+    gc.device = geometry_device;
+    theta = (180.0 - c.theta_deg) * PI / 180.0;  // MP/IO_multiphase.F90:467-468
+    gc.theta = theta;
+    mflbm_solid_node *ps = nullptr;
+    mflbm_fluid_node *pf = nullptr;
+    int32_t ns = 0, nf = 0;
+    int64_t gs = 0, gf = 0;
+    if (mflbm_geometry_preprocess(&gc, walls_global.data(), &ps, &ns, &pf, &nf, &gs, &gf) != MFLBM_OK) {
+        error = std::string("mflbm_geometry_preprocess: ") + mflbm_geometry_last_error();
+        return false;
+    }
+    solid_boundary_nodes.assign(ps, ps + ns);
+    fluid_boundary_nodes.assign(pf, pf + nf);
+    num_solid_boundary_global = gs;
+    num_fluid_boundary_global = gf;
+    mflbm_geometry_free(ps);
+    mflbm_geometry_free(pf);
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // initialisation
 // ---------------------------------------------------------------------------------------------------

@@ -79,6 +79,8 @@ public:
     // fields handed to mflbm_upload
     std::vector<double> f[19], g[19], phi, w_in, f_convec_bc, g_convec_bc, phi_convec_bc;
     // device context
+    bool device_geometry = false;  // true: geometry_preprocessing_new runs on the GPU (mflbm_geometry_preprocess)
+    int geometry_device = -1;
     bool lazy_pdfs = false;  // true: populations are generated one array at a time during upload (large lattices)
     mflbm_ctx *ctx = nullptr;
     std::string error;
@@ -91,7 +93,8 @@ public:
     bool read_walls(const std::string &path);       // MP/Misc.F90:247-295
     void modify_geometry();                         // MP/Misc.F90:213-244
     void set_walls();                               // MP/Misc.F90:6-210 (after walls_global is filled) + pore_profile
-    void geometry_preprocessing_new();              // MP/Geometry_preprocessing.F90:9-512
+    void geometry_preprocessing_new();
+    bool geometry_preprocessing_device();           // same lists from the device kernels (csrc/kernels_geometry.cu)              // MP/Geometry_preprocessing.F90:9-512
     // ---- initialisation ----
     void initialization_basic();                    // initialization_basic_multi / initialization_basic (scalars, w_in)
     void initialization_new();                      // initialization_new_multi(_pdf) / initialization_new(_pdf)

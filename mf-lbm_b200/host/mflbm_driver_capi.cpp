@@ -17,6 +17,10 @@ int mfd_read_parameter(void *h, const char *path) { return ((Driver *)h)->read_p
 int mfd_read_walls(void *h, const char *path) { return ((Driver *)h)->read_walls(path) ? 0 : -1; }
 void mfd_set_idz(void *h, int idz) { ((Driver *)h)->idz = idz; }
 void mfd_set_lazy_pdfs(void *h, int on) { ((Driver *)h)->lazy_pdfs = on != 0; }
+void mfd_set_device_geometry(void *h, int on, int device) {
+    ((Driver *)h)->device_geometry = on != 0;
+    ((Driver *)h)->geometry_device = device;
+}
 
 // walls_global handed over in memory ((1:nx,1:ny,1:nz) int8, i fastest); zero-padded to the lattice like read_walls
 int mfd_set_walls_global(void *h, const int8_t *w, int nxs, int nys, int nzs) {
@@ -52,7 +56,13 @@ void mfd_set_pore_sum(void *h, long long pore_sum) { ((Driver *)h)->pore_sum = p
 int mfd_setup(void *h) {
     Driver *d = (Driver *)h;
     d->set_walls();
-    if (d->c.multiphase) d->geometry_preprocessing_new();
+    if (d->c.multiphase) {
+        if (d->device_geometry) {
+            if (!d->geometry_preprocessing_device()) return -1;
+        } else {
+            d->geometry_preprocessing_new();
+        }
+    }
     d->initialization_basic();
     d->initialization_new();
     return 0;

@@ -121,10 +121,37 @@ def compare_state(ctx, o, tol, fields=("phi", "cn_x", "cn_y", "cn_z", "c_norm", 
         report["f%d" % q] = err(got["f"][q], o.f(q), mq)
         if o.mp:
             report["g%d" % q] = err(got["g"][q], o.g(q), mq)
+    where = {}
     if o.mp:
         for n in fields:
-            report[n] = err(got[n], o.field(n), fl if (n == "curv" and sparse) else None)
+            m = fl if (n == "curv" and sparse) else None
+            if n == "phi" and sparse:
+                m = live_phi_mask(o)
+            report[n] = err(got[n], o.field(n), m)
+            if not (report[n] <= tol):  # first few offending cells, as array indices of the field
+                d = np.abs(got[n] - o.field(n)) > tol * max(1e-300, np.max(np.abs(o.field(n))))
+                if m is not None:
+                    d &= m
+                where[n] = np.argwhere(d)[:6].tolist()
     worst = max(report.values())
     bad = {k: v for k, v in report.items() if not (v <= tol)}
-    assert not bad, "fields beyond tol %g: %s" % (tol, bad)
+    assert not bad, "fields beyond tol %g: %s at %s" % (tol, bad, where)
     return worst
+
+
+def live_phi_mask(o):
+    """phi(-3:n+4)^3 cells with a consumer.  Dead storage: the outermost z ghost planes (k = -3 and k = nz+4) in columns
+    whose boundary node is solid.  The inlet / outlet kernels copy phi(k=0) / phi(k=nz+1) there (wall_indicator blend,
+    MP/Boundary_multiphase_inlet.F90:26-29, _outlet.F90:33-40); the cell is solid, lies outside the solid-boundary list
+    (3 ghost layers) and outside every gradient stencil (K4 runs on -1..n+2), so nothing ever reads it.  Its value is the
+    PREVIOUS step's K3 result of the cell below, which an implementation that skips K3 where phi is uniform cannot (and
+    need not) reproduce."""
+    phi = o.field("phi")
+    m = np.ones(phi.shape, bool)
+    w = o.walls  # (-1:n+2)
+    nz = o.nz
+    lo = w[2:-2, 2:-2, 2 + 0] != 0      # walls(i,j,1), i,j in 1..n
+    hi = w[2:-2, 2:-2, 2 + nz - 1] != 0  # walls(i,j,nz)
+    m[4:-4, 4:-4, 0][lo] = False
+    m[4:-4, 4:-4, -1][hi] = False
+    return m

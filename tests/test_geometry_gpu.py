@@ -72,3 +72,22 @@ def test_degenerate_media_and_errors():
     assert len(solid) == 0 and len(fluid) == 0
     with pytest.raises(M.MflbmError, match="window too small"):
         M.geometry_preprocess(np.zeros((12, 10, 12), np.int8), nzGlobal=64, wk0=20, idz=1, npz=4)
+
+
+def test_host_driver_device_geometry_equals_host_path(tmp_path):
+    """the driver mirror with geometry_preprocessing_new on the GPU hands the hot path the same node lists"""
+    wg = geo.sphere_pack(48, 40, 72, periodic=False, porosity=0.4, rmin=4.0, rmax=9.0, seed=23, buffer=5)
+    ctl = M.write_control_file(str(tmp_path / "ctl.txt"), multiphase=True, lattice_dimensions="48,40,72", MPI_process_num="1,1,1",
+                               external_geometry_read_cmd=1, excluded_layers="5,5")
+    lists = []
+    for dev in (None, 0):
+        drv = M.Driver(ctl, idz=0, walls_window=(wg, 1), device_geometry=dev)
+        drv.setup()
+        lists.append((drv.solid_nodes().copy(), drv.fluid_nodes().copy(), drv.i64("num_solid_boundary_global"),
+                      drv.i64("num_fluid_boundary_global")))
+        drv.close()
+    (s0, f0, gs0, gf0), (s1, f1, gs1, gf1) = lists
+    assert len(s0) > 0 and len(f0) > 0
+    assert s0.tobytes() == s1.tobytes()
+    assert f0.tobytes() == f1.tobytes()
+    assert (gs0, gf0) == (gs1, gf1)

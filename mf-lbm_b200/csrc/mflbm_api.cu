@@ -190,6 +190,8 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         CU(cudaEventCreateWithFlags(&ctx->ev_slab, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_phi, cudaEventDisableTiming));
+        ctx->ev_phi_valid = false;
         Dev &d = ctx->d;
         d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
         d.g.sx = (int)sx; d.g.sxy = (int)sxy; d.g.base = 16; d.g.ntot = (int)ntot;
@@ -276,7 +278,7 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork};
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     delete ctx;
@@ -969,6 +971,8 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
         if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
         if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
     }
+    CU(cudaEventRecord(ctx->ev_phi, s));  // nothing below writes phi at a fluid node (BC: ghost planes, K3: solid nodes)
+    ctx->ev_phi_valid = true;
     launch_bc(ctx, s, odd);
     launch_color_gradient(ctx, s, true);
     return check_launch(ctx);
@@ -1048,9 +1052,18 @@ extern "C" int mflbm_cal_saturation(mflbm_ctx *ctx, double *v1, double *v2) {
     if (!ctx || !v1 || !v2) return fail(ctx, MFLBM_ERR_ARG, "null argument");
     if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
     CU(cudaSetDevice(ctx->device));
-    const int nz = ctx->cfg.nz;
-    const int np = launch_saturation(ctx, ctx->s_main, ctx->red_dev);
-    if (check_launch(ctx) || fetch_red(ctx, 2 * np)) return MFLBM_ERR_CUDA;
+    // Sparse layout: the sum runs over the fluid nodes only, whose phi is final as soon as the collision kernel of the
+    // last step is done -- it does not have to queue behind that step's gradient chain.  It runs on the second stream
+    // after ev_phi and overlaps the (latency-bound, low-occupancy) chain kernels.
+    cudaStream_t st = ctx->s_main;
+    if (ctx->d.sparse && ctx->ev_phi_valid) {
+        st = ctx->s_halo;
+        CU(cudaStreamWaitEvent(st, ctx->ev_phi, 0));
+    }
+    const int np = launch_saturation(ctx, st, ctx->red_dev);
+    if (check_launch(ctx)) return MFLBM_ERR_CUDA;
+    CU(cudaMemcpyAsync(ctx->red_host, ctx->red_dev, 2 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     double a = 0, b = 0;
     for (int k = 0; k < np; k++) { a += ctx->red_host[k]; b += ctx->red_host[np + k]; }
     *v1 = a; *v2 = b;

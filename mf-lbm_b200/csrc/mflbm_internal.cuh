@@ -229,6 +229,8 @@ struct mflbm_ctx {
     int device;
     cudaStream_t s_main, s_halo;
     cudaEvent_t ev_t0, ev_t1, ev_slab, ev_halo, ev_fork;
+    cudaEvent_t ev_phi;      // phi of the fluid nodes of the current step is final (recorded right after the collision kernels)
+    bool ev_phi_valid;
     std::vector<void *> allocs;
     long long bytes;
     long long adj_bytes;  // size of the compressed adjacency

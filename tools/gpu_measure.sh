@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench lines (c3, c2, reference arm), ncu launch lists and full captures of k_collide.
 # usage: tools/gpu_measure.sh TAG   (outputs under gpurun_out/TAG_*)
-TAG=${1:-r01_v8}
+TAG=${1:-r01_v13}
 O=gpurun_out
 mkdir -p $O
 (free -g; nproc; lscpu | grep -E "Model name|Socket|Core|Thread"; nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv) > $O/${TAG}_host.txt 2>&1

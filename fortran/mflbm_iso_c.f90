@@ -89,6 +89,16 @@ module mflbm_c
             import :: c_ptr
             type(c_ptr), value :: list
         end subroutine
+        integer(c_int) function mflbm_output_begin(ctx, what) bind(c, name="mflbm_output_begin")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: what      ! 1 = phi, 2 = u,v,w,rho (after compute_macro_vars), 3 = both
+        end function
+        integer(c_int) function mflbm_output_end(ctx, host) bind(c, name="mflbm_output_end")
+            import :: c_int, c_ptr, mflbm_arrays
+            type(c_ptr), value :: ctx
+            type(mflbm_arrays), intent(in) :: host
+        end function
         integer(c_int) function mflbm_create(cfg, ctx) bind(c, name="mflbm_create")
             import :: c_int, c_ptr, mflbm_config
             type(mflbm_config), intent(in) :: cfg

@@ -160,6 +160,19 @@ long long mflbm_device_bytes(const mflbm_ctx *ctx);
  * torch.distributed in bench.py); replaces MPI_CART_CREATE for the z ring (MP/Mpi_misc.F90:19-38) */
 int mflbm_nccl_unique_id(unsigned char id[128]);
 
+/* ---- asynchronous output staging ----------------------------------------------------------
+ * save_phi / save_macro / VTK_* of the reference (MP/IO_multiphase.F90:646-712, :857-890) do `!$acc update host(...)`
+ * and write files while the device waits.  mflbm_output_begin snapshots the requested fields at the current step into
+ * packed device buffers (for MFLBM_OUT_MACRO after running compute_macro_vars, like save_macro does, MP/Misc.F90:372-430)
+ * and starts the device-to-host copy into pinned memory on a copy stream; it returns at once and the step loop goes
+ * on.  mflbm_output_end waits for that copy and fills the caller's arrays (host->phi, host->u, v, w, rho in the
+ * reference's extents); the Fortran writers then format exactly the arrays they format today.  One output may be in
+ * flight per context. */
+#define MFLBM_OUT_PHI 1
+#define MFLBM_OUT_MACRO 2
+int mflbm_output_begin(mflbm_ctx *ctx, int what);
+int mflbm_output_end(mflbm_ctx *ctx, const mflbm_arrays *host);
+
 /* ---- geometry preprocessing on the device -------------------------------------------------
  * Replaces geometry_preprocessing_new (MP/Geometry_preprocessing.F90:9-512), called from set_walls / the main
  * program before initialization (MP/Main_multiphase.F90:98): classification of the wall array into solid / fluid

@@ -49,7 +49,8 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
            "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
-           "mflbm_tile_stats", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error")
+           "mflbm_tile_stats", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
+           "mflbm_output_begin", "mflbm_output_end")
 
 
 class GeometryConfig(C.Structure):
@@ -116,6 +117,8 @@ def load(strict=False):
     lib.mflbm_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte * 128)]
     lib.mflbm_geometry_preprocess.argtypes = [C.POINTER(GeometryConfig), C.c_void_p, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.mflbm_output_begin.argtypes = [vp, C.c_int]
+    lib.mflbm_output_end.argtypes = [vp, C.POINTER(Arrays)]
     lib.mflbm_geometry_free.argtypes = [vp]
     lib.mflbm_geometry_free.restype = None
     lib.mflbm_geometry_last_error.restype = C.c_char_p
@@ -280,6 +283,20 @@ class Context:
 
     def compute_macro_vars(self):
         self._chk(self.lib.mflbm_compute_macro_vars(self.h), "mflbm_compute_macro_vars")
+
+    OUT_PHI, OUT_MACRO = 1, 2
+
+    def output_begin(self, what):
+        """snapshot phi and / or u,v,w,rho at the current step and start the asynchronous device-to-host copy"""
+        self._chk(self.lib.mflbm_output_begin(self.h, int(what)), "mflbm_output_begin")
+
+    def output_end(self, *names):
+        """wait for the staged output and return {name: ndarray} like download()"""
+        out = {n: np.zeros(field_shape(n, self.nx, self.ny, self.nz), order="F") for n in names}
+        keep = []
+        a = self._arrays(out, keep)
+        self._chk(self.lib.mflbm_output_end(self.h, C.byref(a)), "mflbm_output_end")
+        return out
 
     def monitor(self):
         """Device part of monitor: returns the reference's tk buffer split into named profiles."""

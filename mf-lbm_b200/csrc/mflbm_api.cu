@@ -191,6 +191,9 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         CU(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_phi, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_out_done, cudaEventDisableTiming));
         ctx->ev_phi_valid = false;
         Dev &d = ctx->d;
         d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
@@ -277,8 +280,13 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    for (int f = 0; f < 5; f++) {
+        if (ctx->out_dev[f]) cudaFree(ctx->out_dev[f]);
+        if (ctx->out_host[f]) cudaFreeHost(ctx->out_host[f]);
+    }
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi};
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi, ctx->ev_out, ctx->ev_out_done};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     delete ctx;
@@ -624,15 +632,9 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     for (int q = 0; q < 19; q++) {
         // sparse: array q also holds the compact link slots of direction opc(q) behind the node entries
         const size_t nq = d.sparse ? n + (size_t)d.nlink[OPC(q)] : n;
-        // cudaMalloc hands out 2 MiB-aligned blocks, so element n of all 38 arrays would share its low address bits;
-        // MFLBM_ARRAY_SKEW (bytes, multiple of 256) staggers the array bases (experiment: L2 set conflicts of 76 streams)
-        static const size_t skew = getenv("MFLBM_ARRAY_SKEW") ? (size_t)atol(getenv("MFLBM_ARRAY_SKEW")) / 8 : 0;
-        if (dev_alloc(ctx, &d.f[q], nq + 38 * skew)) return MFLBM_ERR_CUDA;
-        d.f[q] += (size_t)q * skew;
-        if (d.multiphase) {
-            if (dev_alloc(ctx, &d.gg[q], nq + 38 * skew)) return MFLBM_ERR_CUDA;
-            d.gg[q] += (size_t)(19 + q) * skew;
-        }
+        // (staggering the 2 MiB-aligned array bases against L2 set conflicts was measured: no effect, r01_v4)
+        if (dev_alloc(ctx, &d.f[q], nq)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && dev_alloc(ctx, &d.gg[q], nq)) return MFLBM_ERR_CUDA;
     }
     ctx->pdf_alloc = true;
     return 0;
@@ -641,8 +643,6 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
 static int ensure_stage(mflbm_ctx *ctx, size_t bytes) {
     if (ctx->stage_bytes >= bytes) return 0;
     if (ctx->stage) cudaFree(ctx->stage);
-    for (int b = 0; b < 4; b++)
-        if (ctx->halo_buf[b]) cudaFree(ctx->halo_buf[b]);
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
     CU(cudaMalloc((void **)&ctx->stage, bytes));
@@ -1012,6 +1012,65 @@ extern "C" int mflbm_compute_macro_vars(mflbm_ctx *ctx) {
     launch_macro(ctx, ctx->s_main);
     launch_tiles_reset(ctx, ctx->s_main);
     return check_launch(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// asynchronous output staging (include/mflbm.h "asynchronous output staging")
+// ---------------------------------------------------------------------------------------------------
+extern "C" int mflbm_output_begin(mflbm_ctx *ctx, int what) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    Dev &d = ctx->d;
+    if (ctx->out_pending) return fail(ctx, MFLBM_ERR_STATE, "an output is already in flight: call mflbm_output_end first");
+    if (!(what & (MFLBM_OUT_PHI | MFLBM_OUT_MACRO))) return fail(ctx, MFLBM_ERR_ARG, "nothing requested");
+    if ((what & MFLBM_OUT_PHI) && !d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "phi is a multiphase field");
+    const Grid &g = d.g;
+    cudaStream_t s = ctx->s_main;
+    if (what & MFLBM_OUT_MACRO) {  // save_macro computes the macroscopic variables first (MP/IO_multiphase.F90:684)
+        const int rc = mflbm_compute_macro_vars(ctx);
+        if (rc) return rc;
+    } else if (ctx->solid_phi_stale) {  // like mflbm_download: the reference's phi on every listed solid node
+        launch_phi_solid_refresh(ctx, s);
+    }
+    // field f: 0 phi (ghost 4), 1..4 u, v, w, rho (ghost 1)
+    double *src[5] = {d.phi, d.u, d.v, d.w, d.rho};
+    for (int f = 0; f < 5; f++) {
+        const bool want = f == 0 ? (what & MFLBM_OUT_PHI) != 0 : (what & MFLBM_OUT_MACRO) != 0;
+        if (!want) continue;
+        const int o = f == 0 ? 4 : 1;
+        const size_t n = (size_t)(g.nx + 2 * o) * (g.ny + 2 * o) * (g.nz + 2 * o);
+        if (!ctx->out_dev[f]) {
+            CU(cudaMalloc((void **)&ctx->out_dev[f], n * sizeof(double)));
+            CU(cudaMallocHost((void **)&ctx->out_host[f], n * sizeof(double)));
+            ctx->out_elems[f] = n;
+        }
+        launch_repack(ctx, s, src[f], ctx->out_dev[f], o, g.nz + 2 * o, 1 - o, false);  // snapshot in the caller's layout
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_out, s));
+    CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_out, 0));
+    for (int f = 0; f < 5; f++) {
+        const bool want = f == 0 ? (what & MFLBM_OUT_PHI) != 0 : (what & MFLBM_OUT_MACRO) != 0;
+        if (want)
+            CU(cudaMemcpyAsync(ctx->out_host[f], ctx->out_dev[f], ctx->out_elems[f] * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_copy));
+    }
+    CU(cudaEventRecord(ctx->ev_out_done, ctx->s_copy));
+    ctx->out_pending = what & (MFLBM_OUT_PHI | MFLBM_OUT_MACRO);
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_output_end(mflbm_ctx *ctx, const mflbm_arrays *h) {
+    if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->out_pending) return fail(ctx, MFLBM_ERR_STATE, "no output in flight");
+    CU(cudaEventSynchronize(ctx->ev_out_done));
+    double *dst[5] = {h->phi, h->u, h->v, h->w, h->rho};
+    for (int f = 0; f < 5; f++) {
+        const bool have = f == 0 ? (ctx->out_pending & MFLBM_OUT_PHI) != 0 : (ctx->out_pending & MFLBM_OUT_MACRO) != 0;
+        if (have && dst[f]) memcpy(dst[f], ctx->out_host[f], ctx->out_elems[f] * sizeof(double));
+    }
+    ctx->out_pending = 0;
+    return MFLBM_OK;
 }
 
 static int fetch_red(mflbm_ctx *ctx, int n) {

@@ -231,6 +231,12 @@ struct mflbm_ctx {
     cudaEvent_t ev_t0, ev_t1, ev_slab, ev_halo, ev_fork;
     cudaEvent_t ev_phi;      // phi of the fluid nodes of the current step is final (recorded right after the collision kernels)
     bool ev_phi_valid;
+    // asynchronous output staging (mflbm_output_begin / _end): packed device copies, pinned host mirrors, copy stream
+    cudaStream_t s_copy;
+    cudaEvent_t ev_out, ev_out_done;
+    double *out_dev[5], *out_host[5];  // phi, u, v, w, rho in the caller's Fortran layout
+    size_t out_elems[5];
+    int out_pending;                   // field mask of the staged output in flight (0: none)
     std::vector<void *> allocs;
     long long bytes;
     long long adj_bytes;  // size of the compressed adjacency

@@ -1,7 +1,8 @@
 #!/bin/bash
-# One gpurun call: parity tests, then a sweep of kernel tunings (library variants + environment knobs), then ncu captures.
-# usage: tools/sweep.sh TAG
-TAG=${1:-r01_v6}
+# One gpurun call: a sweep of kernel tunings (environment knobs and `make variant` library builds), one short bench line
+# each; the sweeps behind profiles/r01_v3..v6_sweep.txt were produced with earlier lists of this script.
+# usage: tools/sweep.sh TAG            (edit the list at the bottom)
+TAG=${1:-r01_sweep}
 O=gpurun_out
 mkdir -p $O
 L=$O/${TAG}_sweep.log
@@ -22,19 +23,14 @@ counters() {  # label, workload, env...: DRAM / L2 counters of one odd + one eve
   env "$@" timeout 600 ncu --metrics gpu__time_duration.sum,dram__sectors_read.sum,dram__sectors_write.sum,lts__t_sector_op_read_hit_rate.pct,lts__t_sector_op_write_hit_rate.pct,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_write.sum,smsp__inst_executed.sum,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio \
     --clock-control none -k regex:k_collide -s 4 -c 2 --csv --log-file $O/${TAG}_ctr_${label}_${wl}.csv python bench.py --workload $wl --steps 2 --warmup 4 --no-cpu-baseline --no-e2e > $O/${TAG}_ctr_${label}_${wl}.log 2>&1
 }
-timeout 1200 python -m pytest tests -m gpu -q > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $O/${TAG}_pytest.log
-tail -n 5 $O/${TAG}_pytest.log
 run base c3 A=1
-run static_bc_tiles c3 MFLBM_STATIC_BC_TILES=1
-run pf2 c3 MFLBM_PF_DIST=65536 MFLBM_PF_MODE=2
-run pf2_32k c3 MFLBM_PF_DIST=32768 MFLBM_PF_MODE=2
-run blk64 c3 MFLBM_LIB_VARIANT=blk64
-run blk32 c3 MFLBM_LIB_VARIANT=blk32
-run blk64_pf2 c3 MFLBM_LIB_VARIANT=blk64 MFLBM_PF_DIST=65536 MFLBM_PF_MODE=2
 run base c2 A=1
-run pf2 c2 MFLBM_PF_MODE=2
-run blk64 c2 MFLBM_LIB_VARIANT=blk64
-run blk32 c2 MFLBM_LIB_VARIANT=blk32
+run pf64k c3 MFLBM_PF_DIST=65536
+run pf0 c2 MFLBM_PF_DIST=0
+run no_tiles c3 MFLBM_NO_TILES=1
+run static_ghost_tiles c3 MFLBM_STATIC_BC_TILES=1
+run k4_smem c3 MFLBM_K4_SMEM=1
 cat $L
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_c3.csv python bench.py --steps 4 --warmup 6 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_c3.log 2>&1
-ls -la $O
+counters base c3 A=1
+counters base c2 A=1
+ls -la $O | grep $TAG

@@ -48,3 +48,35 @@ def test_rectangular_duct_poiseuille(layout):
         assert np.max(np.abs(wk[fluid] - ref[fluid])) < 1e-2 * ref[fluid].max()
         assert np.all(wk[~fluid] == 0.0)
     ctx.close()
+
+
+@pytest.mark.parametrize("layout", [pytest.param(1, id="dense"), pytest.param(2, id="sparse")])
+def test_laplace_law_static_droplet(layout):
+    """Multiphase path end to end on the GPU (gradient chain with quiet tiles, fused curvature, CSF force, recolouring): a
+    static droplet settles to the Young-Laplace jump dp = 2 gamma / R (p = rho / 3) within 5 %, spurious currents < 1e-4."""
+    from oracle.oracle import Oracle, default_params
+    n, R, gamma = 40, 10.0, 0.03
+    p = default_params(nxG=n, nyG=n, nzG=n, kper=1, inlet_BC=0, outlet_BC=0, la_nu1=0.1, la_nu2=0.1, gamma=gamma, theta_deg=90.0,
+                       n_exclude_inlet=0, n_exclude_outlet=0, initial_fluid_distribution_option=5)
+    o = Oracle(p)
+    o.set_walls(None); o.geometry_preprocess(); o.init_basic(); o.init_phi()
+    c = (n + 1) / 2.0
+    i = np.arange(-3, n + 5)
+    X, Y, Z = np.meshgrid(i, i, i, indexing="ij")
+    o.field("phi")[...] = np.where(np.sqrt((X - c) ** 2 + (Y - c) ** 2 + (Z - c) ** 2) <= R, 1.0, -1.0)
+    o.init_pdf()
+    ctx = ctx_from_oracle(o, kernel_variant=layout)
+    ctx.color_gradient()
+    ctx.run(1, 3000)
+    ctx.compute_macro_vars()
+    got = ctx.download("rho", "phi", "u", "v", "w")
+    rho = got["rho"][1:-1, 1:-1, 1:-1]
+    phi = got["phi"][4:-4, 4:-4, 4:-4]
+    ii = np.arange(1, n + 1)
+    X, Y, Z = np.meshgrid(ii, ii, ii, indexing="ij")
+    r = np.sqrt((X - c) ** 2 + (Y - c) ** 2 + (Z - c) ** 2)
+    dp = (rho[r < R - 4].mean() - rho[(r > R + 4) & (r < R + 8)].mean()) / 3.0
+    r_eff = (3.0 * (0.5 * (1.0 + phi))[r < R + 6].sum() / (4.0 * np.pi)) ** (1.0 / 3.0)
+    assert abs(dp / (2.0 * gamma / r_eff) - 1.0) < 0.05, (dp, r_eff)
+    assert np.sqrt((got["u"] ** 2 + got["v"] ** 2 + got["w"] ** 2).max()) < 1e-4
+    ctx.close()

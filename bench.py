@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 dense, 2 sparse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-geometry", action="store_true",
+                    help="run geometry_preprocessing_new on the host cores (default: on this rank's GPU, mflbm_geometry_preprocess)")
     ap.add_argument("--no-e2e", action="store_true", help="developer sweeps: skip the end-to-end leg (the line then has e2e = null)")
     args = ap.parse_args()
     if args.steps % 2:
@@ -237,11 +239,11 @@ def main():
                                MPI_async_layers_num="0,0,4", external_geometry_read_cmd=0 if spec["geometry"] is None else 1,
                                **spec["control"])
     if spec["geometry"] is None:
-        drv = M.Driver(ctl, idz=rank, lazy_pdfs=True)
+        drv = M.Driver(ctl, idz=rank, lazy_pdfs=True, device_geometry=None if args.host_geometry else local_rank)
     else:
         k0, k1 = M.Driver.window_range(rank, n_gpus, nzG, spec["periodic"]) if n_gpus > 1 else (1, nzG)
         w = geo.sphere_pack_window(nx, ny, nzG, k0, k1, periodic=spec["periodic"], **spec["geometry"])
-        drv = M.Driver(ctl, idz=rank, walls_window=(w, k0), lazy_pdfs=True)
+        drv = M.Driver(ctl, idz=rank, walls_window=(w, k0), lazy_pdfs=True, device_geometry=None if args.host_geometry else local_rank)
         del w
     drv.setup()
     pore_local = drv.i64("pore_sum_local")

@@ -6,12 +6,13 @@
 // Two population layouts share this kernel (template parameter SPARSE):
 //  * dense  : the reference's direct addressing on the padded grid; solid nodes are skipped but their slots
 //             are live storage for bounced populations.
-//  * sparse : populations exist only for ACTIVE nodes (fluid nodes in raster order, then the solid-boundary /
-//             ghost nodes they stream into).  Warps are fully populated with fluid nodes, which is what the
-//             FP64 pipe and the HBM sectors want in porous media (MLUPS counts fluid nodes only,
-//             MP/Main_multiphase.F90:540).  The even step is node-local and needs no addressing at all; the odd
-//             step reads the 18 neighbour indices of the node (coalesced int32 rows).  Same 38 addresses are
-//             read and written per node, so the update stays race-free in any order, like the reference.
+//  * sparse : populations exist only for ACTIVE nodes (fluid nodes in raster order, a thin zone of ghost / solid nodes
+//             at the slab ends, and one compact link slot per fluid node and wall direction).  Warps are fully
+//             populated with fluid nodes, which is what the FP64 pipe and the HBM sectors want in porous media
+//             (MLUPS counts fluid nodes only, MP/Main_multiphase.F90:540).  The even step is node-local and needs
+//             no addressing at all; the odd step decodes the 18 neighbour indices of the node from the warp's
+//             compressed adjacency records (mflbm_internal.cuh), staged through shared memory.  Same 38 addresses
+//             are read and written per node, so the update stays race-free in any order, like the reference.
 #include "collide.cuh"
 #include "gradient.cuh"
 

@@ -152,7 +152,7 @@ struct Dev {
     // The collision kernel reads this one warp-uniform word (address known from n alone) instead of chaining
     // cellA -> tile index -> tquiet -> c_norm; a warp whose stamp is stale skips the c_norm read altogether.
     int *wstamp;             // [ceil(nA/32)]
-    int wq_stamp;            // stamp written by the last k_tile_warps
+    int wq_stamp;            // stamp written by the last tile update (tile_stamp_warps, run by the K4 launch)
     int wq_all;              // 1: every warp counts as active (after a reset, until the next tile update)
     // scalars
     int multiphase, mrt;

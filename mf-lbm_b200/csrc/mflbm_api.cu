@@ -1270,6 +1270,20 @@ extern "C" int mflbmx_adjacency_selftest(int nx, int ny, int nz, const int8_t *w
     g.base = 16;
     g.ntot = 16 + g.sxy * (nz + 8) + 16;
     g.set_magic();
+    {   // the multiply-high cell decomposition must agree with the plain division on every cell of this grid
+        long long bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+        for (long long c = g.base - 4; c < (long long)g.ntot; c++) {
+            unsigned ix, jy, kz;
+            g.coords3((int)c, ix, jy, kz);
+            const unsigned r = (unsigned)(c - (g.base - 4));
+            bad += (kz != r / (unsigned)g.sxy) || (jy != (r % (unsigned)g.sxy) / (unsigned)g.sx) || (ix != (r % (unsigned)g.sxy) % (unsigned)g.sx);
+        }
+        if (bad) {
+            g_err = "Grid::coords3 disagrees with integer division";
+            return MFLBM_ERR_STATE;
+        }
+    }
     HostActive H;
     std::string err;
     if (build_active_host(g, walls, H, err, true)) {

@@ -56,3 +56,13 @@ def test_all_fluid_and_all_solid():
     assert nA == 20 * 12 * 10
     nA, nAct, links, ovf = _selftest(_with_ghosts(np.ones((6, 6, 6), np.int8)))
     assert nA == 0 and links == 0
+
+
+@pytest.mark.parametrize("shape", [(1536, 1536, 2), (1000, 3, 5), (17, 1023, 3), (240, 240, 20), (512, 512, 4)])
+def test_cell_decomposition_on_large_cross_sections(shape):
+    """the self-test also checks Grid::coords3 (multiply-high division by the row / plane strides) on every cell: run it
+    on the cross-sections of the BASELINE configs (strides 1552 x 1544, 256 x 248, 528 x 520) and on awkward ones"""
+    core = np.zeros(shape, np.int8)
+    core[::7, ::5, :] = 1
+    nA, nAct, links, ovf = _selftest(_with_ghosts(core))
+    assert nA == int((core == 0).sum())

@@ -31,14 +31,16 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mflbm.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mflbm.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mflbm_config),sizeof(mflbm_arrays),sizeof(mflbm_solid_node),sizeof(mflbm_fluid_node),'
-                   'offsetof(mflbm_config,la_nui1),offsetof(mflbm_config,nccl_unique_id));return 0;}\n')
+                   'offsetof(mflbm_config,la_nui1),offsetof(mflbm_config,nccl_unique_id),sizeof(mflbm_geometry_config),'
+                   'offsetof(mflbm_geometry_config,theta));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert got == [ctypes.sizeof(M.Config), ctypes.sizeof(M.Arrays), M.SOLID_DTYPE.itemsize, M.FLUID_DTYPE.itemsize,
-                   M.Config.la_nui1.offset, M.Config.nccl_unique_id.offset]
+                   M.Config.la_nui1.offset, M.Config.nccl_unique_id.offset, ctypes.sizeof(M.GeometryConfig),
+                   M.GeometryConfig.theta.offset]
     assert M.SOLID_DTYPE.itemsize == 96 and M.FLUID_DTYPE.itemsize == 48
 
 

@@ -136,7 +136,9 @@ def cpu_reference_run(spec, steps, warmup, sample_n=None):
     geo = import_module("mflbm_b200.geometry")
     mp = spec["multiphase"]
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all host cores: under torchrun only rank 0 runs this leg, and torchrun's OMP_NUM_THREADS=1 default must not stick
+    # (the OpenMP runtime of the oracle library reads the variable when it is loaded, below)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     if spec["geometry"] is None:
         n, nz = spec["nx"], spec["nz"]
         walls = None

@@ -66,3 +66,19 @@ def test_cell_decomposition_on_large_cross_sections(shape):
     core[::7, ::5, :] = 1
     nA, nAct, links, ovf = _selftest(_with_ghosts(core))
     assert nA == int((core == 0).sum())
+
+
+BENTHEIMER = "/root/reference/MF-LBM-extFiles/geometry_files/sample_rock_geometry_wallarray/bentheimer_in10_240_240_240_out10.dat"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(BENTHEIMER), reason="reference fixture not mounted (GPU box)")
+def test_reference_bentheimer_rock_counts_and_adjacency():
+    """The reference's own C2 geometry (240x240x260 Bentheimer sandstone with 10 buffer layers each end; read here only,
+    never copied): 3 670 813 pore nodes (SURVEY 8(c) known answer) through the wall-array reader, and the node numbering /
+    link slots / compressed adjacency of the sparse layout self-check on a real rock."""
+    from oracle.oracle import read_wall_array
+    w = read_wall_array(BENTHEIMER)
+    assert w.shape == (240, 240, 260) and set(np.unique(w)) == {0, 1}
+    assert int((w == 0).sum()) == 3670813
+    nA, nAct, links, ovf = _selftest(_with_ghosts(w))
+    assert nA == 3670813 and links > 0 and nAct >= nA

@@ -68,6 +68,15 @@ def workload_spec(name, n_gpus):
                                  periodic_indicator="0,0,1", excluded_layers="10,10"),
                     label="singlephase_3D absolute-permeability run, Bentheimer-like synthetic %dx%dx%d wall array "
                           "(porosity 0.18 core + 10 fluid layers each end), periodic z, body force" % (n, n, (n + 20) * n_gpus))
+    if name == "c2rock":  # configs[1] on the reference's own Bentheimer wall array (its benchmark cases 6 / 8); one GPU only
+        if n_gpus != 1:
+            raise SystemExit("workload c2rock is a single-GPU case")
+        return dict(multiphase=False, nx=240, ny=240, nz=260, periodic=True, geometry="rock",
+                    walls_file=os.path.join(ROOT, "tests", "golden", "bentheimer_in10_240_out10.bits.xz"),
+                    control=dict(fluid_viscosity=0.1, body_force_0="1d-5", MRT_collision_parameter_preset=1,
+                                 periodic_indicator="0,0,1", excluded_layers="10,10"),
+                    label="singlephase_3D absolute-permeability run on the reference's Bentheimer wall array 240x240x260 "
+                          "(bentheimer_in10_240_240_240_out10.dat, 3 670 813 pore nodes), periodic z, body force")
     if name == "c1":  # configs[0]: the reference's own CPU-runnable case
         return dict(multiphase=True, nx=40, ny=40, nz=60 * n_gpus, periodic=False, geometry=None,
                     control=dict(modify_geometry_cmd=1, breakthrough_check=1),
@@ -145,7 +154,12 @@ def cpu_reference_run(spec, steps, warmup, sample_n=None):
     else:
         n = sample_n or (128 if mp else 160)
         nz = n
-        walls = geo.sphere_pack(n, n, nz, periodic=spec["periodic"], **spec["geometry"])
+        if spec["geometry"] == "rock":  # a central crop of the reference's rock
+            full = geo.load_packed_walls(spec["walls_file"], (spec["nx"], spec["ny"], spec["nz"]))
+            i0, k0 = (spec["nx"] - n) // 2, (spec["nz"] - nz) // 2
+            walls = np.ascontiguousarray(full[i0:i0 + n, i0:i0 + n, k0:k0 + nz])
+        else:
+            walls = geo.sphere_pack(n, n, nz, periodic=spec["periodic"], **spec["geometry"])
     c = spec["control"]
     fl = lambda v: float(str(v).replace("d", "e"))
     kw = dict(multiphase=1 if mp else 0, nxG=n, nyG=n, nzG=nz)
@@ -244,7 +258,10 @@ def main():
         drv = M.Driver(ctl, idz=rank, lazy_pdfs=True, device_geometry=None if args.host_geometry else local_rank)
     else:
         k0, k1 = M.Driver.window_range(rank, n_gpus, nzG, spec["periodic"]) if n_gpus > 1 else (1, nzG)
-        w = geo.sphere_pack_window(nx, ny, nzG, k0, k1, periodic=spec["periodic"], **spec["geometry"])
+        if spec["geometry"] == "rock":
+            w = geo.load_packed_walls(spec["walls_file"], (nx, ny, nzG))
+        else:
+            w = geo.sphere_pack_window(nx, ny, nzG, k0, k1, periodic=spec["periodic"], **spec["geometry"])
         drv = M.Driver(ctl, idz=rank, walls_window=(w, k0), lazy_pdfs=True, device_geometry=None if args.host_geometry else local_rank)
         del w
     drv.setup()

@@ -68,3 +68,13 @@ def sphere_pack_window(nx, ny, nz, k0, k1, porosity=0.36, rmin=8.0, rmax=20.0, s
 
 def sphere_pack(nx, ny, nz, **kw):
     return sphere_pack_window(nx, ny, nz, 1, nz, **kw)
+
+
+def load_packed_walls(path, shape):
+    """Wall array stored one bit per node (i fastest) and lzma-compressed, e.g. tests/golden/bentheimer_in10_240_out10.bits.xz
+    (the reference's own Bentheimer geometry, see tests/golden/make_fixtures.py)."""
+    import lzma
+    with open(path, "rb") as fh:
+        bits = np.frombuffer(lzma.decompress(fh.read()), dtype=np.uint8)
+    n = int(np.prod(shape))
+    return np.unpackbits(bits)[:n].astype(np.int8).reshape(shape, order="F")

@@ -32,6 +32,18 @@ def test_sphere_pack_hits_the_target_porosity():
     assert abs((core == 0).mean() - 0.36) < 0.04  # Boolean model on a small box; the 512^3 realisation lands within 0.005
 
 
+def test_c2rock_workload_reaches_the_driver_with_the_reference_pore_count(tmp_path):
+    """bench.py --workload c2rock: the host side (control file, wall window, set_walls) on the reference's rock"""
+    spec = bench.workload_spec("c2rock", 1)
+    ctl = M.write_control_file(str(tmp_path / "ctl.txt"), multiphase=False, lattice_dimensions="240,240,260", MPI_process_num="1,1,1",
+                               external_geometry_read_cmd=1, **spec["control"])
+    w = geo.load_packed_walls(spec["walls_file"], (240, 240, 260))
+    drv = M.Driver(ctl, idz=0, walls_window=(w, 1), lazy_pdfs=True)
+    drv.setup()
+    assert drv.i64("pore_sum_local") == 3670813
+    drv.close()
+
+
 @pytest.mark.parametrize("name,mp,cross", [("c1", True, (40, 40)), ("c2", False, (240, 240)), ("c3", True, (512, 512)),
                                             ("c5", True, (1536, 1536))])
 def test_workload_table_names_every_baseline_config(name, mp, cross):
@@ -53,3 +65,18 @@ def test_slab_windows_cover_the_preprocessing_stencils():
             assert k0 == 1 or k0 <= lo - 10
             assert k1 == nzG or k1 >= hi + 10
             assert 1 <= k0 <= lo and hi <= k1 <= nzG
+
+
+def test_bentheimer_fixture_is_the_reference_rock():
+    """tests/golden/bentheimer_in10_240_out10.bits.xz (made by tests/golden/make_fixtures.py): 240x240x260, 3 670 813 pore
+    nodes; identical to the reference's file whenever that is mounted."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    w = geo.load_packed_walls(os.path.join(here, "golden", "bentheimer_in10_240_out10.bits.xz"), (240, 240, 260))
+    assert int((w == 0).sum()) == 3670813 and set(np.unique(w)) == {0, 1}
+    # ten open buffer layers at each end inside the x / y side walls of the sample
+    assert np.all(w[1:-1, 1:-1, :10] == 0) and np.all(w[1:-1, 1:-1, -10:] == 0) and np.all(w[0] == 1) and np.all(w[:, 0] == 1)
+    ref = "/root/reference/MF-LBM-extFiles/geometry_files/sample_rock_geometry_wallarray/bentheimer_in10_240_240_240_out10.dat"
+    if os.path.exists(ref):
+        from oracle.oracle import read_wall_array
+        assert np.array_equal(w, read_wall_array(ref))

@@ -229,6 +229,72 @@ bool Driver::read_walls(const std::string &path) {  // MP/Misc.F90:247-295
     return true;
 }
 
+// The reference reads the whole wall array on rank 0 and broadcasts it to every rank (MP/Misc.F90:111-140,
+// MP/Mpi_misc.F90:337-502), which is what stops it at ~1e9 nodes.  Here a rank seeks to the planes
+// [slab - margin, slab + margin] of the same file (clipped at the ends of an open lattice, wrapped on a z-periodic
+// one) and keeps nothing else; set_walls and the geometry preprocessing work on that window (wk0..wk1).
+bool Driver::read_walls_window(const std::string &path, int margin) {
+    FILE *fp = std::fopen(path.c_str(), "rb");
+    if (!fp) {
+        error = "Error! No external geometry file found! Exiting program!";
+        return false;
+    }
+    int32_t dims[3];
+    if (std::fread(dims, 4, 3, fp) != 3) {
+        std::fclose(fp);
+        error = "wall array file: short header";
+        return false;
+    }
+    const int nxs = dims[0], nys = dims[1], nzs = dims[2];
+    const int nxG = c.nxGlobal, nyG = c.nyGlobal, nzG = c.nzGlobal;
+    if (nxG < nxs || nyG < nys || nzG < nzs) {
+        std::fclose(fp);
+        error = "Error! Domain size is smaller than porous media sample size! Exiting program!";
+        return false;
+    }
+    const int nzl = nzG / c.npz;
+    int k0 = idz * nzl + 1 - margin, k1 = idz * nzl + nzl + margin;
+    if (c.kper == 0) {
+        k0 = std::max(k0, 1);
+        k1 = std::min(k1, nzG);
+    }
+    const int nplanes = k1 - k0 + 1;
+    if (c.kper != 0 && nplanes >= nzG) {  // the window would wrap onto itself: hold the whole lattice instead
+        std::fclose(fp);
+        return read_walls(path);
+    }
+    walls_global.assign((size_t)nxG * nyG * nplanes, 0);
+    wk0 = k0;
+    wk1 = k1;
+    const bool pad = c.domain_wall_status_x_max == 1 && c.domain_wall_status_y_max == 1;
+    std::vector<int8_t> row(nxs);
+    for (int kk = 0; kk < nplanes; kk++) {
+        const int k = ((k0 + kk - 1) % nzG + nzG) % nzG + 1;  // source plane, wrapped when periodic
+        int8_t *plane = &walls_global[(size_t)nxG * nyG * kk];
+        if (k <= nzs) {
+            if (std::fseek(fp, 12L + (long)nxs * nys * (long)(k - 1), SEEK_SET) != 0) {
+                std::fclose(fp);
+                error = "wall array file: seek failed";
+                return false;
+            }
+            for (int j = 1; j <= nys; j++) {
+                if (std::fread(row.data(), 1, nxs, fp) != (size_t)nxs) {
+                    std::fclose(fp);
+                    error = "wall array file: short read";
+                    return false;
+                }
+                std::memcpy(plane + (size_t)nxG * (j - 1), row.data(), nxs);
+            }
+        }
+        if (pad)  // same rule as read_walls: solid beyond the sample in x / y
+            for (int j = 1; j <= nyG; j++)
+                for (int i = 1; i <= nxG; i++)
+                    if (j >= nys || i >= nxs) plane[(size_t)(i - 1) + (size_t)nxG * (j - 1)] = 1;
+    }
+    std::fclose(fp);
+    return true;
+}
+
 void Driver::modify_geometry() {  // MP/Misc.F90:213-244
     const int nxG = c.nxGlobal, nyG = c.nyGlobal, nzG = c.nzGlobal;
     const double xc = 0.5 * (double)(nxG + 1), yc = 0.5 * (double)(nyG + 1), zc = 0.5 * (double)(nzG + 1);

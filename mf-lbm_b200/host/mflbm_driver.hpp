@@ -90,7 +90,9 @@ public:
     bool read_parameter(const std::string &path);  // read_parameter_multi / read_parameter + consistency checks
     bool check_parameters();                        // MP/IO_multiphase.F90:455-552 (returns false = mpi_abort in the reference)
     // ---- geometry ----
-    bool read_walls(const std::string &path);       // MP/Misc.F90:247-295
+    bool read_walls(const std::string &path);
+    // only the planes around this rank's slab, straight from the file (no whole-lattice broadcast)
+    bool read_walls_window(const std::string &path, int margin);       // MP/Misc.F90:247-295
     void modify_geometry();                         // MP/Misc.F90:213-244
     void set_walls();                               // MP/Misc.F90:6-210 (after walls_global is filled) + pore_profile
     void geometry_preprocessing_new();

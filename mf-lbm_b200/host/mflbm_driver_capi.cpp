@@ -15,6 +15,7 @@ const char *mfd_error(void *h) { return ((Driver *)h)->error.c_str(); }
 
 int mfd_read_parameter(void *h, const char *path) { return ((Driver *)h)->read_parameter(path) ? 0 : -1; }
 int mfd_read_walls(void *h, const char *path) { return ((Driver *)h)->read_walls(path) ? 0 : -1; }
+int mfd_read_walls_window(void *h, const char *path, int margin) { return ((Driver *)h)->read_walls_window(path, margin) ? 0 : -1; }
 void mfd_set_idz(void *h, int idz) { ((Driver *)h)->idz = idz; }
 void mfd_set_lazy_pdfs(void *h, int on) { ((Driver *)h)->lazy_pdfs = on != 0; }
 void mfd_set_device_geometry(void *h, int on, int device) {

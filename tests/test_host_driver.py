@@ -121,3 +121,30 @@ def test_windowed_geometry_matches_whole_lattice(tmp_path):
             _same_lists(dw, o)
             assert dw.i64("pore_sum_local") == int((o.walls[2:-2, 2:-2, 2:-2] == 0).sum())
             dw.close()
+
+
+@pytest.mark.parametrize("kper", [0, 1])
+def test_windowed_wall_file_read_equals_the_whole_file_path(tmp_path, kper):
+    """every rank reads only the planes around its slab from the reference wall-array file (seek, no
+    whole-lattice array, no broadcast) and ends up with exactly the local walls, pore counts and boundary-node lists that
+    the whole-file path produces.  The sample is smaller than the lattice in x / y (the reference pads it with solid)."""
+    from importlib import import_module
+    geo = import_module("mflbm_b200.geometry")
+    nxs, nys, nzG, npz = 36, 30, 96, 4
+    sample = geo.sphere_pack(nxs, nys, nzG, periodic=bool(kper), porosity=0.5, rmin=3.0, rmax=7.0, seed=31, buffer=0 if kper else 4)
+    wf = M.write_wall_array(str(tmp_path / "walls.dat"), sample)
+    over = dict(lattice_dimensions="40,34,%d" % nzG, MPI_process_num="1,1,%d" % npz, external_geometry_read_cmd=1,
+                excluded_layers="0,0")
+    if kper:
+        over.update(periodic_indicator="0,0,1", inlet_BC=0, outlet_BC=0)
+    ctl = M.write_control_file(str(tmp_path / "ctl.txt"), multiphase=True, **over)
+    for idz in range(npz):
+        a = M.Driver(ctl, idz=idz, wall_file=wf)
+        b = M.Driver(ctl, idz=idz, wall_file=wf, wall_file_window=True)
+        a.setup(); b.setup()
+        assert np.array_equal(a.walls, b.walls)
+        assert a.i64("pore_sum_local") == b.i64("pore_sum_local")
+        assert a.solid_nodes().tobytes() == b.solid_nodes().tobytes()
+        assert a.fluid_nodes().tobytes() == b.fluid_nodes().tobytes()
+        assert np.array_equal(a.field("phi"), b.field("phi"))
+        a.close(); b.close()

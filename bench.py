@@ -51,6 +51,17 @@ def workload_spec(name, n_gpus):
                                  excluded_layers="10,10"),
                     label="multiphase_3D scCO2/brine drainage, synthetic random-sphere-pack %dx%dx%d (porosity 0.36, "
                           "10 buffer layers each end), velocity inlet / convective outlet" % (n, n, n * n_gpus))
+    if name == "c4":  # configs[3]: STRONG scaling, the 512x512x1024 lattice (flow axis z) cut into n_gpus slabs
+        if 1024 % n_gpus:
+            raise SystemExit("workload c4 needs a GPU count that divides 1024")
+        return dict(multiphase=True, nx=512, ny=512, nz=1024, periodic=False, scaling="strong",
+                    geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=2, buffer=10),
+                    control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
+                                 RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
+                                 initial_interface_position=8.0, initial_fluid_distribution_option=1,
+                                 excluded_layers="10,10"),
+                    label="multiphase_3D strong scaling, synthetic sphere pack 512x512x1024 (porosity 0.36, 10 buffer layers "
+                          "each end) in %d z-slab(s) of %d planes, velocity inlet / convective outlet" % (n_gpus, 1024 // n_gpus))
     if name == "c5":  # configs[4]: one 1536x1536x192 slab per GPU (N = 8 is the 1536^3 weak-scaling target), same physics as C3
         return dict(multiphase=True, nx=1536, ny=1536, nz=192 * n_gpus, periodic=False,
                     geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=3, buffer=10),
@@ -343,7 +354,7 @@ def main():
     if rank == 0:
         out = {
             "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": spec.get("scaling", "weak"), "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": spec["label"], "fluid_nodes": pore_global, "porosity": pore_global / float(nx * ny * nzG),
                        "per_gpu_lattice": "%dx%dx%d" % (nx, ny, nz), "parallelism": "z-slab x%d" % n_gpus,

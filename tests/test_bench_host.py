@@ -54,6 +54,12 @@ def test_workload_table_names_every_baseline_config(name, mp, cross):
     assert bench.BYTES_PER_UPDATE[True] == 624.0 and bench.BYTES_PER_UPDATE[False] == 304.0
 
 
+def test_strong_scaling_workload_keeps_the_global_lattice():
+    for n in (1, 2, 4, 8):
+        s = bench.workload_spec("c4", n)  # BASELINE configs[3]
+        assert (s["nx"], s["ny"], s["nz"]) == (512, 512, 1024) and s["scaling"] == "strong"
+
+
 def test_slab_windows_cover_the_preprocessing_stencils():
     """Driver.window_range: every slab's window reaches the lattice end or extends >= 10 planes beyond the slab, which is
     what mflbm_geometry_preprocess demands (classification radius 1 + four smoothing passes + ISO8 radius 2)."""

@@ -148,3 +148,32 @@ def test_windowed_wall_file_read_equals_the_whole_file_path(tmp_path, kper):
         assert a.fluid_nodes().tobytes() == b.fluid_nodes().tobytes()
         assert np.array_equal(a.field("phi"), b.field("phi"))
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("option", [1, 2, 3, 4, 5])
+def test_initial_fluid_distributions_match_oracle(tmp_path, option):
+    """initialization_new_multi, every deterministic initial_fluid_distribution_option (MP/Init_multiphase.F90:243-330;
+    option 6 draws unseeded random numbers in the reference and is injected from the host instead)."""
+    rng = np.random.default_rng(40 + option)
+    wg = (rng.random((16, 14, 24)) < 0.2).astype(np.int8)
+    d = _driver(tmp_path, walls=wg, lattice_dimensions="16,14,24", initial_fluid_distribution_option=option,
+                initial_interface_position=7.0, excluded_layers="2,2")
+    o = make_oracle(nxG=16, nyG=14, nzG=24, walls_global=wg, initial_fluid_distribution_option=option, interface_z0=7.0,
+                    n_exclude_inlet=2, n_exclude_outlet=2)
+    assert np.array_equal(d.field("phi"), o.field("phi"))
+    for q in range(19):
+        assert np.array_equal(d.field("f", q), o.f(q)) and np.array_equal(d.field("g", q), o.g(q))
+    d.close()
+
+
+@pytest.mark.parametrize("inlet,outlet", [(1, 1), (2, 2), (1, 2)])
+def test_boundary_condition_setups_match_oracle(tmp_path, inlet, outlet):
+    """initialization_basic_multi for the velocity / pressure inlet-outlet combinations: derived scalars and the inlet
+    profile (MP/Init_multiphase.F90:116-236, MP/Misc.F90:625-665)."""
+    d = _driver(tmp_path, modify_geometry_cmd=1, inlet_BC=inlet, outlet_BC=outlet)
+    o = make_oracle(modify_geometry_cmd=1, inlet_BC=inlet, outlet_BC=outlet)
+    for n in ("la_nui1", "la_nui2", "phi_inlet", "force_Z", "uin_avg", "flowrate", "rho_in", "rho_out", "relaxation"):
+        assert d.f64(n) == o.get_double(n), n
+    assert np.array_equal(d.field("w_in"), o.field("w_in"))
+    assert np.array_equal(d.field("phi"), o.field("phi"))
+    d.close()

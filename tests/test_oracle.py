@@ -202,3 +202,21 @@ def test_laplace_law_static_droplet():
     umax = np.sqrt((o.field("u") ** 2 + o.field("v") ** 2 + o.field("w") ** 2).max())
     assert umax < 1e-4
     o.close()
+
+
+def test_velocity_inlet_injects_the_prescribed_flow_rate():
+    """inlet_bounce_back_velocity_BC (MP/Boundary_multiphase_inlet.F90:6-102): on C1 the volumetric flow through the first
+    slices settles to flowrate = uin_avg * A_xy = 1.083 within 0.5 %, and the whole column carries it within
+    2 % (weak compressibility) -- an independent known answer for the inlet kernel, the flow monitor and the w_in profile."""
+    o = Oracle(default_params(modify_geometry_cmd=1), fast=True)
+    o.setup(None)
+    o.color_gradient()
+    for n in range(1, 2001):
+        o.step(n)
+    o.monitor()
+    fl = o.field("fl1") + o.field("fl2")
+    target = o.get_double("flowrate")
+    assert target == pytest.approx(1.083, rel=1e-12)
+    assert np.max(np.abs(fl[:4] / target - 1.0)) < 5e-3
+    assert np.max(np.abs(fl / target - 1.0)) < 2e-2
+    o.close()

@@ -1021,6 +1021,7 @@ extern "C" int mflbm_output_begin(mflbm_ctx *ctx, int what) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
     CU(cudaSetDevice(ctx->device));
     Dev &d = ctx->d;
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_output_begin before mflbm_upload");
     if (ctx->out_pending) return fail(ctx, MFLBM_ERR_STATE, "an output is already in flight: call mflbm_output_end first");
     if (!(what & (MFLBM_OUT_PHI | MFLBM_OUT_MACRO))) return fail(ctx, MFLBM_ERR_ARG, "nothing requested");
     if ((what & MFLBM_OUT_PHI) && !d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "phi is a multiphase field");

@@ -6,9 +6,13 @@
 
 One "step" = one call of main_iteration_kernel (mflbm_step): collision+streaming of every fluid node, halo exchange,
 inlet/outlet kernels and colour gradient.  MLUPS counts fluid (pore) nodes only, like the reference's benchmark
-(MP/Main_multiphase.F90:540).  Default workload at N=1: BASELINE.json configs[2], the multiphase 512^3 sphere-pack
-drainage (the largest single-GPU configuration of the headline, multiphase, metric); N>1 stacks one such 512^3 slab
-per GPU along z (weak scaling).  ``--workload c2`` is configs[1] (singlephase 240^3 Bentheimer-like, periodic z).
+(MP/Main_multiphase.F90:540).  Default workload for every N: BASELINE.json configs[4], one 1536x1536x192 multiphase
+sphere-pack slab per GPU (the largest single-GPU configuration, 97 GB; N = 8 is the 1536^3 weak-scaling target); the
+slabs are identical packs stacked along z, so every GPU holds the same number of fluid nodes.  ``--workload c3`` is
+configs[2] (512^3 per GPU), ``c4`` configs[3] (strong scaling 512x512x1024), ``c2`` / ``c2rock`` configs[1] (singlephase
+240x240x260, synthetic / the reference's Bentheimer rock).  After the headline region (drainage front next to the
+inlet) the multiphase workloads are timed again in two interface-rich states (``roofline_active``); N>1 first checks
+N slabs == single-domain oracle bit for bit on small cases (``parity_ngpu``).
 
 The GPU arm never touches oracle/: geometry, node lists and initial fields come from the host driver mirror
 (mf-lbm_b200/host), everything per step from libmflbm.so through the C ABI.  The CPU oracle is only executed for
@@ -43,14 +47,15 @@ def workload_spec(name, n_gpus):
     if name == "c3":  # configs[2] (N=1) / weak-scaling stack (N>1), SURVEY 8(d) C3/C5 physics
         n = int(os.environ.get("MFLBM_BENCH_N", "512"))
         por = float(os.environ.get("MFLBM_BENCH_POROSITY", "0.36"))  # developer knob; the BASELINE config is 0.36
-        return dict(multiphase=True, nx=n, ny=n, nz=n * n_gpus, periodic=False,
+        return dict(multiphase=True, nx=n, ny=n, nz=n * n_gpus, periodic=False, unit_nz=n,
                     geometry=dict(porosity=por, rmin=8.0, rmax=20.0, seed=1, buffer=10),
                     control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
                                  RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
                                  initial_interface_position=8.0, initial_fluid_distribution_option=1,
                                  excluded_layers="10,10"),
                     label="multiphase_3D scCO2/brine drainage, synthetic random-sphere-pack %dx%dx%d (porosity 0.36, "
-                          "10 buffer layers each end), velocity inlet / convective outlet" % (n, n, n * n_gpus))
+                          "10 buffer layers each end%s), velocity inlet / convective outlet" % (
+                              n, n, n * n_gpus, "" if n_gpus == 1 else "; %d identical %d-plane packs stacked along z" % (n_gpus, n)))
     if name == "c4":  # configs[3]: STRONG scaling, the 512x512x1024 lattice (flow axis z) cut into n_gpus slabs
         if 1024 % n_gpus:
             raise SystemExit("workload c4 needs a GPU count that divides 1024")
@@ -63,14 +68,15 @@ def workload_spec(name, n_gpus):
                     label="multiphase_3D strong scaling, synthetic sphere pack 512x512x1024 (porosity 0.36, 10 buffer layers "
                           "each end) in %d z-slab(s) of %d planes, velocity inlet / convective outlet" % (n_gpus, 1024 // n_gpus))
     if name == "c5":  # configs[4]: one 1536x1536x192 slab per GPU (N = 8 is the 1536^3 weak-scaling target), same physics as C3
-        return dict(multiphase=True, nx=1536, ny=1536, nz=192 * n_gpus, periodic=False,
+        return dict(multiphase=True, nx=1536, ny=1536, nz=192 * n_gpus, periodic=False, unit_nz=192,
                     geometry=dict(porosity=0.36, rmin=8.0, rmax=20.0, seed=3, buffer=10),
                     control=dict(fluid1_viscosity=0.004, fluid2_viscosity=0.04, surface_tension=0.03, theta=30,
                                  RK_beta=0.95, inlet_BC=1, outlet_BC=1, capillary_number="100d-6",
                                  initial_interface_position=8.0, initial_fluid_distribution_option=1,
                                  excluded_layers="10,10"),
-                    label="multiphase_3D weak-scaling slab 1536x1536x%d (%d x 192 planes, sphere pack porosity 0.36, 10 buffer "
-                          "layers at the lattice ends), velocity inlet / convective outlet" % (192 * n_gpus, n_gpus))
+                    label="multiphase_3D weak scaling towards 1536^3: 1536x1536x%d = %d identical 192-plane sphere packs stacked "
+                          "along z (porosity 0.36 core + 10 fluid layers at each end of every pack, so each GPU holds the same "
+                          "number of fluid nodes), velocity inlet / convective outlet" % (192 * n_gpus, n_gpus))
     if name == "c2":  # configs[1]
         n = int(os.environ.get("MFLBM_BENCH_N", "240"))
         return dict(multiphase=False, nx=n, ny=n, nz=(n + 20) * n_gpus, periodic=True,
@@ -203,13 +209,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--workload", default="c5", help="c5 (default: one 1536x1536x192 slab per GPU, BASELINE configs[4] and the largest "
+                    "single-GPU configuration), c3 (512^3 per GPU, configs[2]), c4 (strong scaling 512x512x1024, configs[3]), "
+                    "c2 / c2rock (singlephase 240x240x260, configs[1]), c1 (tube+sphere, configs[0])")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 dense, 2 sparse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-geometry", action="store_true",
                     help="run geometry_preprocessing_new on the host cores (default: on this rank's GPU, mflbm_geometry_preprocess)")
     ap.add_argument("--no-e2e", action="store_true", help="developer sweeps: skip the end-to-end leg (the line then has e2e = null)")
+    ap.add_argument("--state", default="drainage", choices=["drainage", "random"],
+                    help="developer / profiling: 'random' re-initialises with the seeded option-6 phase field BEFORE the headline region")
+    ap.add_argument("--no-active", action="store_true", help="skip the interface-rich second timed regions (roofline_active = null)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the N-slab == single-domain parity check before the timed region")
     args = ap.parse_args()
     if args.steps % 2:
         args.steps += 1  # AA pattern: keep odd/even parity across rounds like the reference (MP/Main_multiphase.F90:510)
@@ -257,6 +269,10 @@ def main():
     dist = rk.dist
     allreduce = rk.allreduce
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_ngpu(rk, M, local_rank)  # N slabs == single-domain oracle, checked before anything is timed
+
     nx, ny, nzG = spec["nx"], spec["ny"], spec["nz"]
     nz = nzG // n_gpus
     t_setup = time.time()
@@ -271,6 +287,8 @@ def main():
         k0, k1 = M.Driver.window_range(rank, n_gpus, nzG, spec["periodic"]) if n_gpus > 1 else (1, nzG)
         if spec["geometry"] == "rock":
             w = geo.load_packed_walls(spec["walls_file"], (nx, ny, nzG))
+        elif spec.get("unit_nz") and n_gpus > 1:  # weak scaling: every GPU holds the same pack (equal fluid-node counts)
+            w = geo.stacked_window(nx, ny, spec["unit_nz"], k0, k1, **spec["geometry"])
         else:
             w = geo.sphere_pack_window(nx, ny, nzG, k0, k1, periodic=spec["periodic"], **spec["geometry"])
         drv = M.Driver(ctl, idz=rank, walls_window=(w, k0), lazy_pdfs=True, device_geometry=None if args.host_geometry else local_rank)
@@ -295,35 +313,46 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    # warm-up
-    drv.run(1, args.warmup)
-    barrier()
-    launches0 = drv.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    drv.profile(True)
-    # timed region: EXACTLY args.steps steps, device-timed (CUDA events on the compute stream), max over ranks
-    barrier()
-    drv.timer_start()
-    drv.run(1, args.steps)
-    ms = drv.timer_stop()
-    barrier()
-    coll_ms, coll_launches = drv.profile_read()
-    drv.profile(False)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = drv.launch_count - launches0
-    ntile, nquiet = drv.tile_stats()
-    ms = allreduce(ms, "max")
-    mlups = pore_global * args.steps / (ms * 1e-3) / 1e6
+    def timed_region(steps, warmup, clocks=False):
+        """warm-up, then EXACTLY `steps` steps device-timed with CUDA events on the compute stream (max over ranks), the
+        collision-kernel launches event-timed on their own stream inside it"""
+        drv.run(1, warmup)
+        barrier()
+        launches0 = drv.launch_count
+        sampler = ClockSampler(local_rank) if (clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        drv.profile(True)
+        barrier()
+        drv.timer_start()
+        drv.run(1, steps)
+        ms_local = drv.timer_stop()
+        barrier()
+        coll_ms, coll_launches = drv.profile_read()
+        drv.profile(False)
+        r = dict(ms_local=ms_local, ms=allreduce(ms_local, "max"), coll_ms=coll_ms, coll_launches=coll_launches,
+                 launches=drv.launch_count - launches0, clocks=sampler.stop() if sampler else None)
+        nt, nq = drv.tile_stats()
+        r["quiet"] = (nq / nt) if nt else None
+        r["mlups"] = pore_global * steps / (r["ms"] * 1e-3) / 1e6
+        r["achieved"] = bpu * pore_local * steps / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else 0.0
+        r["step_frac"] = r["mlups"] * 1e6 * bpu / 1e9 / (peak * n_gpus)
+        return r
 
-    # roofline of the dominant kernel (k_collide): algorithmic bytes of the launches / their event-timed duration
-    coll_bytes = bpu * pore_local * args.steps
-    achieved = coll_bytes / (coll_ms * 1e-3) / 1e9 if coll_ms > 0 else 0.0
+    if mp and args.state == "random":
+        drv.reinitialize(6, seed=20261018)
+        drv.color_gradient()
+        drv.sync()
+    main_r = timed_region(args.steps, args.warmup, clocks=True)
+    ms, mlups, achieved = main_r["ms"], main_r["mlups"], main_r["achieved"]
+    per_rank_ms = rk.allgather(main_r["ms_local"] / args.steps)
+    per_rank_pore = rk.allgather(float(pore_local))
+
+    # ncu DRAM bytes per k_collide launch: only when a capture of exactly this workload / lattice / GPU count was kept
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("%s/%dx%dx%d/n%d" % (args.workload, nx, ny, nz, n_gpus), {}).get("dram_bytes_per_launch")
 
     # e2e through the C ABI with HOST buffers: per step H2D of the step's host input (inlet profile w_in, pinned),
     # mflbm_step, and a D2H read of the step's result (saturation partial sums via mflbm_cal_saturation / flow monitor)
@@ -350,26 +379,57 @@ def main():
     h2d = (nx + 2) * (ny + 2) * 8
     d2h = 2 * nz * 8 if mp else 0
 
+    # interface-rich regimes (the timed state above is a drainage front next to the inlet: most tiles are quiet)
+    active = None
+    if mp and not args.no_active:
+        ksteps = max(2, (args.steps // 2) & ~1)
+        # (i) same state, quiet-tile skipping switched off: the colour-gradient chain runs on every node
+        drv.set_parameter("quiet_tiles", 0)
+        drv.color_gradient()
+        r1 = timed_region(ksteps, 4)
+        drv.set_parameter("quiet_tiles", 1)
+        # (ii) the reference's own benchmark state (test_suites/3D_simulation/6.performance_benchmarking:
+        # initial_fluid_distribution_option 6, per-node random phi at target_fluid1_saturation 0.4), seeded here
+        t_re = time.time()
+        drv.reinitialize(6, seed=20261018)
+        drv.color_gradient()
+        drv.sync()
+        t_re = time.time() - t_re
+        r2 = timed_region(args.steps, args.warmup)
+        active = {
+            "no_quiet_tiles": {"ms_per_step": r1["ms"] / ksteps, "mlups": r1["mlups"], "frac": r1["achieved"] / peak,
+                               "step_frac": r1["step_frac"], "kernel_ms_per_step": r1["coll_ms"] / ksteps, "steps": ksteps,
+                               "state": "the drainage state of the headline region, quiet-tile skipping off (mflbm_set_parameter quiet_tiles 0)"},
+            "ms_per_step": r2["ms"] / args.steps, "mlups": r2["mlups"], "frac": r2["achieved"] / peak, "step_frac": r2["step_frac"],
+            "kernel_ms_per_step": r2["coll_ms"] / args.steps, "quiet_tile_fraction": r2["quiet"], "steps": args.steps,
+            "warmup": args.warmup, "reinit_s": round(t_re, 1), "gpu_launches": int(r2["launches"]),
+            "state": "initial_fluid_distribution_option 6: per-node random phi = +-1 at saturation 0.4 (seeded hash of the global "
+                     "node position), the state of the reference's benchmark case 6; interface everywhere, no quiet tile"}
+
     out = None
     if rank == 0:
         out = {
             "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": spec.get("scaling", "weak"), "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": spec["label"], "fluid_nodes": pore_global, "porosity": pore_global / float(nx * ny * nzG),
+            "config": {"workload": spec["label"], "workload_key": args.workload, "fluid_nodes": pore_global,
+                       "porosity": pore_global / float(nx * ny * nzG),
                        "per_gpu_lattice": "%dx%dx%d" % (nx, ny, nz), "parallelism": "z-slab x%d" % n_gpus,
                        "l2_policy": "working set per step (%.1f GB) >> 126 MB L2, no flush needed" % (drv.device_bytes / 1e9),
                        "population_layout": "auto (kernel_variant=%d)" % args.variant, "setup_s": round(setup_s, 1),
                        "device_bytes_per_gpu": drv.device_bytes,
-                       "quiet_tile_fraction": (nquiet / ntile) if ntile else None},
+                       "quiet_tile_fraction": main_r["quiet"], "state": args.state,
+                       "fluid_nodes_per_rank": [int(v) for v in per_rank_pore],
+                       "ms_per_step_per_rank": [round(v, 4) for v in per_rank_ms]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_collide (collision + AA streaming)", "peak_source": peak_src,
-                         "bytes_per_update": bpu, "kernel_ms_per_step": coll_ms / args.steps, "kernel_launches": coll_launches,
-                         "step_frac_of_roofline": mlups * 1e6 * bpu / 1e9 / (peak * n_gpus)},
+                         "bytes_per_update": bpu, "kernel_ms_per_step": main_r["coll_ms"] / args.steps,
+                         "kernel_launches": main_r["coll_launches"], "step_frac_of_roofline": main_r["step_frac"]},
+            "roofline_active": active,
             "e2e": None if args.no_e2e else {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / max(e2e_steps, 1), "host_wall_ms_per_step": wall_e2e / max(e2e_steps, 1),
                     "what": "per step: mflbm_upload(w_in, pinned host) + mflbm_step + mflbm_cal_saturation read-back"},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(main_r["launches"]), "clocks": main_r["clocks"], "parity_ngpu": parity}
     drv.close()
     if rank == 0:
         if n_gpus == 1 and not args.no_cpu_baseline:
@@ -380,6 +440,66 @@ def main():
         print(json.dumps(out))
     rk.close()
     return 0
+
+
+def parity_ngpu(rk, M, local_rank):
+    """N-slab == single-domain parity on this job's N GPUs (the cases of tests/test_multi_gpu.py, stretched to 16 planes
+    per slab): every rank runs one z slab of a small lattice with the STRICT (-fmad=false) library and the NCCL halo
+    exchange, and compares the populations, phi and the interface normal of its slab bit for bit with a single-domain
+    run of the CPU oracle.  Checker leg: the oracle is test infrastructure and is never timed or shipped."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import ctx_from_oracle, make_oracle
+    npz, idz = rk.world, rk.rank
+    nzG = 16 * npz
+    cases = {
+        "mp_open": dict(nxG=20, nyG=18, nzG=nzG, la_nu2=0.04, interface_z0=6.0, n_exclude_inlet=0, n_exclude_outlet=0),
+        "mp_periodic": dict(nxG=20, nyG=18, nzG=nzG, kper=1, force_z0=2e-4, la_nu2=0.04, initial_fluid_distribution_option=5,
+                            interface_z0=6.0, n_exclude_inlet=0, n_exclude_outlet=0),
+        "sp_periodic": dict(multiphase=0, nxG=20, nyG=18, nzG=nzG, kper=1, force_z0=1e-5, la_nu1=0.1, n_exclude_inlet=0,
+                            n_exclude_outlet=0),
+    }
+    steps = 9
+    rng = np.random.default_rng(3)
+    wg = (rng.random((20, 18, nzG)) < 0.25).astype(np.int8)
+    wg[:, :, :3] = 0
+    wg[:, :, -3:] = 0
+    bad_total, names = 0, []
+    for name in sorted(cases):
+        for layout in (2, 1):
+            ref = make_oracle(walls_global=wg, **cases[name])  # single domain
+            if ref.mp:
+                ref.color_gradient()
+            for t in range(1, steps + 1):
+                ref.step(t)
+            o = make_oracle(walls_global=wg, npz=npz, idz=idz, **cases[name])  # this rank's slab: initial state only
+            nid = rk.broadcast_bytes(M.nccl_unique_id() if idz == 0 else b"", 128)
+            ctx = ctx_from_oracle(o, strict=True, kernel_variant=layout, device=local_rank, use_nccl=1, nccl_unique_id=nid)
+            if o.mp:
+                ctx.color_gradient()
+            ctx.run(1, steps)
+            ctx.sync()
+            got = ctx.download(*(["f"] + (["g", "phi", "cn_x", "cn_y", "cn_z", "c_norm"] if o.mp else [])))
+            nzl = nzG // npz
+            ks = slice(idz * nzl, (idz + 1) * nzl)
+            fluid = (ref.walls[2:-2, 2:-2, 2:-2] == 0)[:, :, ks]
+            bad = 0
+            for q in range(19):
+                bad += int(np.count_nonzero(got["f"][q][1:-1, 1:-1, 1:-1][fluid] != ref.f(q)[1:-1, 1:-1, 1:-1][:, :, ks][fluid]))
+                if o.mp:
+                    bad += int(np.count_nonzero(got["g"][q][1:-1, 1:-1, 1:-1][fluid] != ref.g(q)[1:-1, 1:-1, 1:-1][:, :, ks][fluid]))
+            if o.mp:
+                bad += int(np.count_nonzero(got["phi"][4:-4, 4:-4, 4:-4][fluid] != ref.field("phi")[4:-4, 4:-4, 4:-4][:, :, ks][fluid]))
+                for nm in ("cn_x", "cn_y", "cn_z", "c_norm"):
+                    bad += int(np.count_nonzero(got[nm][2:-2, 2:-2, 2:-2][fluid] != ref.field(nm)[2:-2, 2:-2, 2:-2][:, :, ks][fluid]))
+            ctx.close()
+            o.close()
+            ref.close()
+            bad = int(round(rk.allreduce(float(bad))))
+            bad_total += bad
+            names.append("%s/%s:%s" % (name, "sparse" if layout == 2 else "dense", "ok" if bad == 0 else "%d mismatches" % bad))
+    return {"cases": names, "slabs": npz, "steps": steps, "lattice": "20x18x%d" % nzG, "bit_exact": bad_total == 0,
+            "mismatched_values": bad_total, "library": "libmflbm_strict.so (-fmad=false)",
+            "reference": "single-domain CPU oracle (oracle/, checker only)"}
 
 
 if __name__ == "__main__":

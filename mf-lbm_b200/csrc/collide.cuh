@@ -126,10 +126,10 @@ __device__ __forceinline__ void mrt_core(double (&ft)[19], double den, double fx
 }
 
 // Multiphase node update.  a = fluid-1 incoming populations, b = fluid-2; both are overwritten with
-// the recoloured post-collision populations.  K = curv*c_norm is passed pre-multiplied in the
-// reference's order (0.5*gamma*curv*c_norm).  Returns phi.
+// the recoloured post-collision populations.  tmp0 = 0.5*gamma*curv*c_norm evaluated in the reference's order
+// (MP/Kernel_multiphase.F90:118) by the caller.  Returns phi.
 __device__ __forceinline__ double collide_mp(const Dev &P, double (&a)[19], double (&b)[19], double cnx, double cny, double cnz,
-                                             double curv, double c_norm) {
+                                             double tmp0) {
     double ft[19];
 #pragma unroll
     for (int q = 0; q < 19; q++) ft[q] = a[q] + b[q];
@@ -138,7 +138,7 @@ __device__ __forceinline__ double collide_mp(const Dev &P, double (&a)[19], doub
     const double rho2 = b[0] + b[1] + b[2] + b[3] + b[4] + b[5] + b[6] + b[7] + b[8] + b[9] + b[10] + b[11] + b[12] + b[13] +
                         b[14] + b[15] + b[16] + b[17] + b[18];
     const double phi = (rho1 - rho2) / (rho1 + rho2);
-    double tmp = 0.5 * P.gamma * curv * c_norm;
+    double tmp = tmp0;
     const double fx = tmp * cnx, fy = tmp * cny, fz = tmp * cnz + P.force_Z;
     const double omega = 1.0 / (6.0 / ((1.0 + phi) * P.la_nui1 + (1.0 - phi) * P.la_nui2) + 0.5);
     Rates r;

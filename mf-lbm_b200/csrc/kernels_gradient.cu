@@ -33,7 +33,10 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
     const double *__restrict__ ph = P.phi;
     auto v = [&](int a, int b, int d) { return ph[c + a + sx * b + sxy * d]; };
     const double gx = ddx(v), gy = ddy(v), gz = ddz(v);
-    const double cn = sqrt(gx * gx + gy * gy + gz * gz);
+    const double s2 = gx * gx + gy * gy + gz * gz;
+    // sqrt is monotonic and correctly rounded: s2 < 0.99e-12 implies sqrt(s2) < 1e-6, so the (slow, FP64) square root is
+    // only taken where the outcome of the reference's cut-off test can depend on it.  Most cells of an active tile are bulk.
+    const double cn = s2 < 0.99e-12 ? 0.0 : sqrt(s2);
     if (cn < 1e-6) {
         // LAZY (sparse layout): bulk nodes already hold zeros; c_norm == 0 implies n == 0 at non-solid nodes
         if (LAZY && P.c_norm[c] == 0.0) return;
@@ -290,6 +293,7 @@ __device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int sta
 #define MFLBM_K4_ROW 24  // shared-memory row pitch in doubles (10 used): 8 mod 16 keeps half-warps conflict-free
 __global__ void __launch_bounds__(128) k_gradient_tiles(const Dev P, int stamp) {
     __shared__ double sphi[6 * 6 * MFLBM_K4_ROW];
+    if (P.tcount[2]) return;  // most tiles active: the flat kernels run instead
     const int count = P.tcount[0];
     const int sx = P.g.sx, sxy = P.g.sxy;
     const int tid = threadIdx.x;
@@ -334,12 +338,14 @@ __global__ void k_tile_all(const Dev P) {
     if (t == 0) {
         P.tcount[0] = P.ntiles;
         P.tcount[1] = P.ntiles;
+        P.tcount[2] = 1;
     }
 }
 
 // tile-driven launch shape: persistent blocks walk a tile list; the threads of a block share the entries of one tile
 template <int K>
 __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp) {
+    if (P.tcount[2]) return;  // most tiles active: k_chain_flat<K> runs instead
     const int *__restrict__ list = K == 3 ? P.tk3 : P.tact;
     const int count = P.tcount[K == 3 ? 1 : 0];
     const int *__restrict__ start = (K == 3 || K == 6) ? P.ts_start : (K == 4 ? P.tg_start : P.tf_start);
@@ -354,6 +360,64 @@ __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp) {
             else cn_solid_at(P, e);
         }
     }
+}
+
+// Which shape runs the chain of this step, decided on the device right after k_tile_update: when more than a quarter of
+// the tiles are active (interface-rich states, e.g. the reference's benchmark case 6 with random phi) walking tile lists
+// with one 64-thread block per tile wastes most lanes on short CSR ranges (measured on C3, random phi: K3..K6 5.8 ms
+// tile-driven); the flat kernels below then sweep the whole node lists with full warps.  Both shapes are always
+// launched, the one that is not selected returns at once (fixed grid-stride grids, so an idle launch costs microseconds).
+// Evaluating a quiet tile anyway is exact: it reproduces the zeros / the K3 means the skipped evaluation would give.
+__global__ void k_tile_mode(const Dev P) { P.tcount[2] = (long long)P.tcount[0] * 4 > (long long)P.ntiles ? 1 : 0; }
+
+template <int K>
+__global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
+    if (!P.tcount[2]) return;
+    const int count = (K == 3 || K == 6) ? P.num_solid : (K == 4 ? P.nG : P.num_fluid);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        if (K == 3) phi_solid_at(P, e);
+        else if (K == 4) gradient_at<true>(P, P.gcell[e]);
+        else if (K == 5) alter_at(P, e);
+        else cn_solid_at(P, e);
+    }
+}
+
+// K7 + packing (Dev::G): one thread per fluid node of every ACTIVE warp (32 consecutive A nodes).  The blocks scan the
+// warp stamps 32 at a time (one per lane, ballot) so that quiet warps cost one coalesced word each; all = 1 skips the scan.
+__global__ void __launch_bounds__(256) k_gradient_pack(const Dev P, int all) {
+    const int lane = threadIdx.x & 31;
+    const int nW = (P.nA + 31) >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+    if (!all && P.use_tiles) all = P.tcount[2];
+    for (int w0 = gw * 32; w0 < nW; w0 += tw * 32) {
+        unsigned m = 0xffffffffu;
+        if (!all) m = __ballot_sync(0xffffffffu, w0 + lane < nW && P.wstamp[w0 + lane] == P.wq_stamp);
+        else if (w0 + 32 > nW) m = nW - w0 >= 32 ? 0xffffffffu : ((1u << (nW - w0)) - 1u);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int n = ((w0 + b) << 5) + lane;
+            if (n >= P.nA) continue;
+            const int c = P.cellA[n];
+            const double cnorm = P.c_norm[c];
+            double cnx = 0.0, cny = 0.0, cnz = 0.0, tmp = 0.0;
+            if (cnorm != 0.0) {  // c_norm == 0: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature (exact zeros)
+                cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
+                tmp = 0.5 * P.gamma * curvature_at(P, c) * cnorm;  // MP/Kernel_multiphase.F90:118, MP/Phase_gradient.F90:116-200
+            }
+            P.G[0][n] = cnx; P.G[1][n] = cny; P.G[2][n] = cnz; P.G[3][n] = tmp;
+        }
+    }
+}
+
+void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.multiphase || !P.sparse || P.nA <= 0) return;
+    const int all = (!P.use_tiles || P.wq_all) ? 1 : 0;
+    int nb = (P.nA + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    k_gradient_pack<<<nb, 256, 0, st>>>(P, all);
+    c->launches++;
 }
 
 // every tile active: after create / upload / compute_macro_vars / an explicit mflbm_color_gradient
@@ -411,33 +475,49 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
     if (P.use_tiles) {
         const int nb = (P.ntiles + 127) / 128;
         if (stepping) {
-            cudaMemsetAsync(P.tcount, 0, 2 * sizeof(int), st);
+            cudaMemsetAsync(P.tcount, 0, 4 * sizeof(int), st);
             k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp);
+            k_tile_mode<<<1, 1, 0, st>>>(P);
             P.wq_stamp = c->tile_stamp;
             P.wq_all = 0;
             P.tile_cur ^= 1;
             c->solid_phi_stale = true;
         } else {
             launch_tiles_reset(c, st);
-            k_tile_all<<<nb, 128, 0, st>>>(P);
+            k_tile_all<<<nb, 128, 0, st>>>(P);  // tcount[2] = 1: the flat kernels run
             c->solid_phi_stale = false;
         }
         const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
-        // K4 also stamps the warps of the active tiles (stepping only; nG > 0 whenever there is a fluid node)
-        if (P.num_solid > 0) k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0);
-        if (P.nG > 0) {
-            if (P.k4_smem) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, stepping ? c->tile_stamp : 0);
-            else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, stepping ? c->tile_stamp : 0);
+        const int fgrid = 148 * 8;
+        // K4 (tile-driven) also stamps the warps of the active tiles (stepping only; nG > 0 whenever there is a fluid node)
+        if (P.num_solid > 0) {
+            if (stepping) k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0);
+            k_chain_flat<3><<<fgrid, 256, 0, st>>>(P);
         }
-        if (P.num_fluid > 0) k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0);
-        if (P.num_solid > 0) k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0);
-        c->launches += 1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0);
+        if (P.nG > 0) {
+            if (stepping) {
+                if (P.k4_smem) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
+                else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, c->tile_stamp);
+            }
+            k_chain_flat<4><<<fgrid, 256, 0, st>>>(P);
+        }
+        if (P.num_fluid > 0) {
+            if (stepping) k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0);
+            k_chain_flat<5><<<fgrid, 256, 0, st>>>(P);
+        }
+        if (P.num_solid > 0) {
+            if (stepping) k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0);
+            k_chain_flat<6><<<fgrid, 256, 0, st>>>(P);
+        }
+        c->launches += (stepping ? 2 : 1) * (1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0));
+        launch_gradient_pack(c, st);
         return;
     }
     if (P.num_solid > 0) {
         k_phi_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
         c->launches++;
     }
+    c->solid_phi_stale = false;
     if (P.sparse) {
         if (P.nG > 0) {
             k_gradient_list<<<(P.nG + 127) / 128, 128, 0, st>>>(P);
@@ -456,7 +536,8 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
         k_cn_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
         c->launches++;
     }
-    if (!P.sparse) launch_curvature(c, st);  // sparse layout: evaluated inside the collision kernel
+    if (!P.sparse) launch_curvature(c, st);  // sparse layout: evaluated by k_gradient_pack for the fluid nodes
+    else launch_gradient_pack(c, st);
 }
 
 }  // namespace mflbm

@@ -34,21 +34,22 @@ __device__ __forceinline__ void stpop(double *p, double v) { *p = v; }
 // Collision of one node in registers (a = fluid 1 / the single fluid, b = fluid 2), including what surrounds it on the
 // multiphase path: interface normal / curvature inputs, the phi store and the per-tile phi classes.
 template <bool MP, bool SPARSE>
-__device__ __forceinline__ void collide_node(const Dev &P, const int c, const int wst, double (&a)[19], double (&b)[19]) {
+__device__ __forceinline__ void collide_node(const Dev &P, const int n, const int c, const int wst, double (&a)[19], double (&b)[19]) {
     if (MP) {
-        // c_norm == 0 (no interface nearby: n = 0 and F = 0.5*gamma*curv*0 = 0 whatever the curvature) lets the sparse
-        // layout skip the normal loads and the curvature stencil.  Exact: the skipped terms are +-0.
-        // Quiet tile (uniform phi around, see kernels_gradient.cu): c_norm is known to be 0 without reading it.
-        const bool quiet = SPARSE && P.use_tiles && !P.wq_all && wst != P.wq_stamp;  // warp-uniform
-        const double c_norm = quiet ? 0.0 : P.c_norm[c];
-        double cnx = 0.0, cny = 0.0, cnz = 0.0, curv = 0.0;
+        double cnx = 0.0, cny = 0.0, cnz = 0.0, tmp = 0.0;
         if (!SPARSE) {
-            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c]; curv = P.curv[c];
-        } else if (c_norm != 0.0) {
             cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
-            curv = curvature_at(P, c);  // K7 evaluated here from the neighbours' normals instead of a stored field
+            tmp = 0.5 * P.gamma * P.curv[c] * P.c_norm[c];
+        } else {
+            // Quiet warp (every node in a tile with uniform phi around, see kernels_gradient.cu): n = 0 and F = 0 are known
+            // without reading anything.  Otherwise four coalesced reads of the packed gradient (Dev::G); the skipped terms
+            // of a node without interface are exact zeros there.
+            const bool quiet = P.use_tiles && !P.wq_all && wst != P.wq_stamp;  // warp-uniform
+            if (!quiet) {
+                cnx = P.G[0][n]; cny = P.G[1][n]; cnz = P.G[2][n]; tmp = P.G[3][n];
+            }
         }
-        const double phi = collide_mp(P, a, b, cnx, cny, cnz, curv, c_norm);
+        const double phi = collide_mp(P, a, b, cnx, cny, cnz, tmp);
         P.phi[c] = phi;
         if (SPARSE && P.use_tiles) {
             // record the phi class of this node's tile: consecutive lanes mostly share (tile, class), so the first lane
@@ -65,7 +66,6 @@ __device__ __forceinline__ void collide_node(const Dev &P, const int c, const in
     } else {
         collide_sp(P, a);
     }
-
 }
 
 // One node: gather the incoming populations, collide, scatter.  n = active index (sparse layout), c = dense cell,
@@ -140,7 +140,7 @@ __device__ __forceinline__ void node_update(const Dev &P, const int n, const int
         }
     }
 
-    collide_node<MP, SPARSE>(P, c, wst, a, b);
+    collide_node<MP, SPARSE>(P, n, c, wst, a, b);
 
     if (ODD) {  // push q into slot opc(q) of x + e_q (MP/Kernel_multiphase.F90:318-354)
         const int cl = SPARSE ? n : c;
@@ -191,7 +191,11 @@ __global__ void __launch_bounds__(collide_block(MP), collide_resident(MP)) k_col
         }
         if (n < n0 || n >= n1) return;
         c = P.cellA[n];
-        if (MP) wst = P.use_tiles ? P.wstamp[n >> 5] : 0;
+        if (MP && P.use_tiles) {
+            const int all = __ldg(P.tcount + 2);  // the last gradient chain ran over every tile: every warp is active
+            const int w = P.wstamp[n >> 5];       // (two independent loads)
+            wst = all ? P.wq_stamp : w;
+        }
     } else {
         const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
         const int j = blockIdx.y + 1;

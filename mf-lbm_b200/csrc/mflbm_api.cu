@@ -636,6 +636,9 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
         if (dev_alloc(ctx, &d.f[q], nq)) return MFLBM_ERR_CUDA;
         if (d.multiphase && dev_alloc(ctx, &d.gg[q], nq)) return MFLBM_ERR_CUDA;
     }
+    if (d.sparse && d.multiphase)
+        for (int m = 0; m < 4; m++)
+            if (dev_alloc(ctx, &d.G[m], (size_t)d.nA + 64)) return MFLBM_ERR_CUDA;
     ctx->pdf_alloc = true;
     return 0;
 }
@@ -758,7 +761,7 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             mask[n] = m;
             law[n] = s.la_weight;
         }
-        if (d.use_tiles) {  // group by tile for the tile-driven chain (entries are independent of each other)
+        if (d.tcls[0]) {  // group by tile for the tile-driven chain (entries are independent of each other)
             std::vector<int> tile(d.num_solid), order, start;
             for (int n = 0; n < d.num_solid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
             sort_by_tile(tile, d.ntiles, order, start);
@@ -787,7 +790,7 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             nw[5 * n + 3] = cos(s.theta);  // dcos/dsin of MP/Phase_gradient.F90:238-242, evaluated once by the host libm
             nw[5 * n + 4] = sin(s.theta);
         }
-        if (d.use_tiles) {
+        if (d.tcls[0]) {
             std::vector<int> tile(d.num_fluid), order, start;
             for (int n = 0; n < d.num_fluid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
             sort_by_tile(tile, d.ntiles, order, start);
@@ -1195,6 +1198,16 @@ extern "C" int mflbm_set_parameter(mflbm_ctx *ctx, const char *name, double valu
     else if (!strcmp(name, "phi_inlet")) d.phi_inlet = value;
     else if (!strcmp(name, "sa_inject")) d.sa_inject = value;
     else if (!strcmp(name, "relaxation")) d.relaxation = value;
+    else if (!strcmp(name, "quiet_tiles")) {
+        // developer / measurement switch: 0 = evaluate the colour-gradient chain on every node (no quiet-tile skipping),
+        // 1 = back to the default.  Results are identical either way; only contexts that were set up with tiles can switch.
+        if (!d.tcls[0]) return fail(ctx, MFLBM_ERR_STATE, "this context has no quiet-tile state (dense layout, singlephase or MFLBM_NO_TILES)");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->s_main));
+        d.use_tiles = value != 0.0 ? 1 : 0;
+        d.wq_all = 1;
+        ctx->tiles_static_ready = false;
+    }
     else return fail(ctx, MFLBM_ERR_ARG, std::string("unknown parameter ") + name);
     return MFLBM_OK;
 }

@@ -128,6 +128,12 @@ struct Dev {
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
     int nG;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
+    // sparse multiphase layout: what the collision kernel needs of the colour gradient, PACKED by active index n so that a
+    // warp reads four coalesced 256-byte rows: G[0..2] = interface normal n (after K4 + K5), G[3] = 0.5*gamma*curv*|grad phi|
+    // (the reference's `tmp`, MP/Kernel_multiphase.F90:118, evaluated in its order).  Written after every gradient chain by
+    // k_gradient_pack (K7 lives there: 54 gathers per interface node with few registers and full occupancy, instead of
+    // inside the 128-register collision kernel); exact zeros wherever |grad phi| = 0.
+    double *G[4];
     // phi-uniformity tiles (sparse multiphase layout, DESIGN.md "Quiet tiles"): the padded grid is cut into tiles of
     // 8x4x4 cells; the collision kernel records which phi classes occur among the fluid nodes of each tile
     // (P: |phi-1|<=1e-7, M: |phi+1|<=1e-7, X: anything else).  A tile whose 27-tile neighbourhood shows one single
@@ -146,7 +152,8 @@ struct Dev {
     unsigned char *tquiet;   // 1: tile is quiet
     int *tg_start, *ts_start, *tf_start;  // [ntiles+1] CSR ranges of gcell / the solid list / the fluid list (sorted by tile)
     int *tact, *tk3;         // [ntiles] active tiles (K4,K5,K6) / tiles within one tile of an active tile (K3), per step
-    int *tcount;             // [2] lengths of tact, tk3
+    int *tcount;             // [4] lengths of tact, tk3; [2] = 1: most tiles are active, the chain of this step ran over the
+                             // whole lists (flat, grid-stride) and every warp counts as active; [3] unused
     int *tk3stamp;           // [ntiles] step stamp guarding the tk3 append
     // per warp of 32 consecutive A nodes: stamp of the last tile update that found one of its nodes in an ACTIVE tile.
     // The collision kernel reads this one warp-uniform word (address known from n alone) instead of chaining
@@ -280,6 +287,7 @@ void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st);
 void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);
 int tiles_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_curvature(mflbm_ctx *c, cudaStream_t st);
+void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
 void launch_macro(mflbm_ctx *c, cudaStream_t st);

@@ -41,6 +41,16 @@ class Ranks:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allgather(self, x):
+        """one float64 per rank -> list over ranks (per-rank fluid-node counts and step times)"""
+        if self.dist is None:
+            return [float(x)]
+        import torch
+        t = self._tensor([0.0] * self.world, torch.float64)
+        t[self.rank] = float(x)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu().tolist()]
+
     def broadcast_bytes(self, payload, nbytes, src=0):
         """rank src's bytes object to every rank (the NCCL unique id of the slab ring)"""
         if self.dist is None:

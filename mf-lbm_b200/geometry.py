@@ -66,6 +66,16 @@ def sphere_pack_window(nx, ny, nz, k0, k1, porosity=0.36, rmin=8.0, rmax=20.0, s
     return out
 
 
+def stacked_window(nx, ny, unit_nz, k0, k1, **kw):
+    """Planes k0..k1 of a lattice made of identical copies of ONE unit_nz-plane sphere pack (its buffer layers included)
+    stacked along z: plane k of the stack is plane ((k-1) mod unit_nz)+1 of the unit.  Every z slab of unit_nz planes
+    then holds exactly the same medium (equal fluid-node counts: weak-scaling numbers compare communication, not
+    porosity drift)."""
+    unit = sphere_pack_window(nx, ny, unit_nz, 1, unit_nz, **kw)
+    idx = [(k - 1) % unit_nz for k in range(k0, k1 + 1)]
+    return np.ascontiguousarray(unit[:, :, idx]) if idx != list(range(unit_nz)) else unit
+
+
 def sphere_pack(nx, ny, nz, **kw):
     return sphere_pack_window(nx, ny, nz, 1, nz, **kw)
 

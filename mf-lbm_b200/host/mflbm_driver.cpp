@@ -786,18 +786,52 @@ bool Driver::create_context(int device, int use_nccl, const unsigned char *nccl_
     return true;
 }
 
-bool Driver::upload() {
+// initial_fluid_distribution_option 6 (MP/Init_multiphase.F90:306-311) with a SEEDED generator: the reference draws
+// random_number() per node after an unseeded random_seed() (irreproducible); here the draw is a hash of
+// the node's GLOBAL position, so every z-slab decomposition sees the same field.  phi = 1 where u <= sa_target.
+void Driver::random_phase_field(unsigned long long seed) {
+    const V4 v4{(size_t)nx + 8, (size_t)ny + 8};
+    phi.assign((size_t)(nx + 8) * (ny + 8) * (nz + 8), 0.0);
+    const long long nzG = c.nzGlobal;
+#pragma omp parallel for collapse(2)
+    for (int k = -3; k <= nz + 4; k++)
+        for (int j = -3; j <= ny + 4; j++)
+            for (int i = -3; i <= nx + 4; i++) {
+                long long z = (long long)idz * nz + k;
+                if (c.kper) z = ((z - 1) % nzG + nzG) % nzG + 1;
+                unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)((i + 3) + (long long)(nx + 8) * ((j + 3) + (long long)(ny + 8) * (z + 3)) + 1);
+                x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;  // splitmix64 finaliser
+                x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+                x ^= x >> 31;
+                const double u = (double)(x >> 11) * (1.0 / 9007199254740992.0);
+                phi[v4(i, j, k)] = u > c.sa_target ? -1.0 : 1.0;
+            }
+}
+
+// start over from a new initial fluid distribution on the SAME geometry: initialization_new_multi again, then the
+// fields (phi, populations, convective-outlet state) go to the existing context; walls and node lists stay
+bool Driver::reinitialize(int option, unsigned long long seed) {
+    if (!ctx) { error = "reinitialize before create_context"; return false; }
+    c.initial_fluid_distribution_option = option;
+    if (option == 6) random_phase_field(seed);
+    initialization_new();
+    return upload(false);
+}
+
+bool Driver::upload(bool with_geometry) {
     mflbm_arrays a;
     std::memset(&a, 0, sizeof a);
-    a.walls = walls.data();
+    if (with_geometry) a.walls = walls.data();
     a.w_in = w_in.data();
     a.f_convec_bc = f_convec_bc.data();
     if (c.multiphase) {
         a.phi = phi.data();
         a.g_convec_bc = g_convec_bc.data();
         a.phi_convec_bc = phi_convec_bc.data();
-        a.solid_boundary_nodes = solid_boundary_nodes.data();
-        a.fluid_boundary_nodes = fluid_boundary_nodes.data();
+        if (with_geometry) {
+            a.solid_boundary_nodes = solid_boundary_nodes.data();
+            a.fluid_boundary_nodes = fluid_boundary_nodes.data();
+        }
     }
     if (!lazy_pdfs) {
         for (int q = 0; q < 19; q++) {

@@ -102,7 +102,9 @@ public:
     void initialization_new();                      // initialization_new_multi(_pdf) / initialization_new(_pdf)
     // ---- device ----
     bool create_context(int device, int use_nccl, const unsigned char *nccl_id, int kernel_variant);
-    bool upload();
+    bool upload(bool with_geometry = true);
+    void random_phase_field(unsigned long long seed);      // option 6 with a seeded, decomposition-independent draw
+    bool reinitialize(int option, unsigned long long seed);  // new initial fluid distribution on the same geometry
     bool main_iteration_kernel(int ntime);          // MP/Main_multiphase.F90:341-486 -> mflbm_step
     bool color_gradient();                          // MP/Phase_gradient.F90:5 -> mflbm_color_gradient
     bool monitor(int ntime, MonitorResult *out, const std::string &outdir);  // MP/Monitor.F90:5-277 (np==1 tail)

@@ -128,7 +128,7 @@ def lower_outside_strings(s):
 # expressions
 # ----------------------------------------------------------------------------------------------------------------
 TOKEN = re.compile(r"""\s*(?:
-    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?) |
+    (?P<num>(?:\d+\.(?![a-z]+\.)\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?) |
     (?P<dotop>\.(?:and|or|not|eq|ne|lt|le|gt|ge|eqv|neqv|true|false)\.) |
     (?P<id>[a-z_]\w*) |
     (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*") |
@@ -251,6 +251,8 @@ class Parser:
             else:
                 e = self.power()  # right associative
             m = re.fullmatch(r"\(?(\d+)\)?", e)
+            if m and re.fullmatch(r"[a-z_]\w*", base) and self.ctx.is_int(base):
+                return "f_ipow(%s, %d)" % (base, int(m.group(1)))  # integer ** integer stays integer arithmetic (and wraps)
             if m:  # integer power: repeated multiplication like gfortran's expansion of x**2 / x**3
                 n = int(m.group(1))
                 if n == 2:
@@ -353,9 +355,13 @@ C_RESERVED = {"auto", "break", "case", "char", "const", "continue", "default", "
 
 
 class Ctx:
-    def __init__(self, arrays):
+    def __init__(self, arrays, ints=()):
         self.arrays = arrays  # names known to be arrays (module level + current locals)
         self.local_arrays = set()
+        self.ints = set(ints)  # integer scalars (module level + current locals / arguments)
+
+    def is_int(self, name):
+        return name in self.ints
 
     def is_array(self, name):
         return name in self.arrays or name in self.local_arrays
@@ -597,7 +603,8 @@ def omp_pragma(text, ctx):
 
 
 def translate_sub(sub, mod, known_subs, openmp):
-    ctx = Ctx(set(mod.arrays) | {n for n, *_ in mod.parrays} | {m for t in mod.types.values() for m, _, d in t if d})
+    ctx = Ctx(set(mod.arrays) | {n for n, *_ in mod.parrays} | {m for t in mod.types.values() for m, _, d in t if d},
+              {n for n, ct in mod.scalars.items() if ct in ("int", "signed char", "short", "long long")})
     decls, code, ind = [], [], 1
     argtypes = {}
     locals_ = {}
@@ -608,22 +615,30 @@ def translate_sub(sub, mod, known_subs, openmp):
     def emit(s):
         code.append("    " * ind + s)
 
-    for kind, s in sub.body:
+    def one(kind, s):
+        nonlocal ind, pending_omp
         if kind == "omp":
             if openmp:
                 p = omp_pragma(s, ctx)
                 if p:
                     pending_omp = p
-            continue
-        if s.startswith("use ") or s == "implicit none" or s.startswith("include ") or s == "save" or s.startswith("external "):
-            continue
+            return
+        if s.startswith("use ") or s.startswith("use,") or s == "implicit none" or s.startswith("include ") or s == "save" or s.startswith("external "):
+            return
+        m = re.match(r"^(integer|logical|real\s*\(kind=8\)|double precision)\s+([a-z_]\w*(?:\s*,\s*[a-z_]\w*)*)$", s)
+        if m and "::" not in s:  # old-style declaration without '::'
+            s = "%s :: %s" % (m.group(1), m.group(2))
         if s.startswith("character"):
-            continue
+            return
         d = parse_decl(s) if "::" in s or DECL.match(s) and not re.match(r"^(integer|real|logical)\s*\(", s.split("=")[0] if "=" in s and "::" not in s else "x") else None
         if d is not None and ("::" in s):
             if d["ctype"] is None:
-                continue
+                return
             for name, dims, init in d["entities"]:
+                if not dims and d["ctype"] in ("int", "signed char", "short", "long long"):
+                    ctx.ints.add(name)
+                else:
+                    ctx.ints.discard(name)  # a local of another type shadows a module integer
                 if name in sub.args:
                     if dims:
                         raise Unsupported("array dummy argument %s" % name)
@@ -645,22 +660,22 @@ def translate_sub(sub, mod, known_subs, openmp):
                     locals_[name] = (d["ctype"], None)
                     if init is not None:
                         raise Unsupported("initialised local %s (implies SAVE)" % name)
-            continue
+            return
         # ---- executable statements ----
         if s == "return":
             emit("return;")
-            continue
+            return
         if s in ("continue",):
-            continue
+            return
         if s == "exit":
             emit("break;")
-            continue
+            return
         if s == "cycle":
             emit("continue;")
-            continue
+            return
         if s.startswith("stop"):
             emit("ref_abort(\"%s: stop\");" % sub.name)
-            continue
+            return
         m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", s)
         if m:
             v = ctx.cname(m.group(1))
@@ -677,40 +692,40 @@ def translate_sub(sub, mod, known_subs, openmp):
             assigned.add(m.group(1))
             ind += 1
             stack.append("do")
-            continue
+            return
         m = re.match(r"^do\s+while\s*\((.*)\)$", s)
         if m:
             emit("while (%s) {" % cexpr(m.group(1), ctx))
             ind += 1
             stack.append("do")
-            continue
+            return
         if re.match(r"^end\s*do$", s):
             ind -= 1
             emit("}")
             stack.pop()
-            continue
+            return
         m = re.match(r"^if\s*\((.*)\)\s*then$", s)
         if m:
             emit("if (%s) {" % cexpr(m.group(1), ctx))
             ind += 1
             stack.append("if")
-            continue
+            return
         m = re.match(r"^else\s*if\s*\((.*)\)\s*then$", s)
         if m:
             ind -= 1
             emit("} else if (%s) {" % cexpr(m.group(1), ctx))
             ind += 1
-            continue
+            return
         if s == "else":
             ind -= 1
             emit("} else {")
             ind += 1
-            continue
+            return
         if re.match(r"^end\s*if$", s):
             ind -= 1
             emit("}")
             stack.pop()
-            continue
+            return
         pending_omp = None
         m = re.match(r"^if\s*\(", s)
         if m:  # one-line if: find the matching parenthesis
@@ -723,8 +738,17 @@ def translate_sub(sub, mod, known_subs, openmp):
             cond, rest = s[s.index("(") + 1:j], s[j + 1:].strip()
             inner = translate_simple(rest, ctx, sub, known_subs, assigned)
             emit("if (%s) { %s }" % (cexpr(cond, ctx), inner))
-            continue
-        emit(translate_simple(s, ctx, sub, known_subs, assigned))
+            return
+        try:
+            emit(translate_simple(s, ctx, sub, known_subs, assigned))
+        except Unsupported as e:
+            raise Unsupported("%s  [in: %s]" % (e, s[:80]))
+
+    for kind, s in sub.body:
+        try:
+            one(kind, s)
+        except Unsupported as e:
+            raise Unsupported(str(e) if "[in:" in str(e) else "%s  [in: %s]" % (e, s[:90]))
     if stack:
         raise Unsupported("unbalanced blocks in %s" % sub.name)
     for a in sub.args:
@@ -747,6 +771,14 @@ def translate_simple(s, ctx, sub, known_subs, assigned):
     if m:
         name, args = m.group(1), m.group(2)
         a = [cexpr(x, ctx) for x in split_top(args)] if args and args.strip() else []
+        if name == "random_seed":
+            return "/* random_seed(): unseeded in the reference; random_number itself is not provided */;"
+        if name in ("mpi_barrier", "mpi_bcast"):
+            return "/* %s: nothing to do in a single process */;" % name
+        if name in ("mpi_reduce", "mpi_allreduce"):  # one rank: the reduction of a scalar is a copy (arrays: not supported)
+            if len(a) >= 3 and a[2] == "1" and not ctx.is_array(split_top(args)[1].strip()):
+                return "%s = %s; /* %s over one rank */" % (a[1], a[0], name)
+            raise Unsupported("%s of an array" % name)
         known_subs.setdefault("__called__", set()).add(name)
         return "%s(%s);" % (name, ", ".join(a))
     if re.match(r"^(print|write)\b", s):
@@ -798,8 +830,10 @@ double tanh(double); double acos(double); double atan(double); double pow(double
 double floor(double); double ceil(double); double copysign(double, double);
 void *calloc(size_t, size_t); void free(void *); int printf(const char *, ...); void abort(void); int strcmp(const char *, const char *);
 static void ref_abort(const char *why) { printf("oracle/_ref: %s\n", why); abort(); }
+#define mpi_status_size 6 /* mpif.h stand-in: only sizes the (unused) status arrays of MemAllocate_multi */
 #define f_sq(x) ((x) * (x))
 #define f_cube(x) ((x) * (x) * (x))
+static int f_ipow(int b, int e) { unsigned r = 1u, x = (unsigned)b; while (e > 0) { if (e & 1) r *= x; x *= x; e >>= 1; } return (int)r; }
 static double f_powi(double x, int n) { double r = 1.0; int m = n < 0 ? -n : n; while (m) { if (m & 1) r *= x; x *= x; m >>= 1; } return n < 0 ? 1.0 / r : r; }
 #define f_abs(x) _Generic((x), int: f_iabs, signed char: f_iabs, short: f_iabs, long long: f_labs, float: f_fabsf, default: fabs)(x)
 static int f_iabs(int x) { return x < 0 ? -x : x; }
@@ -909,8 +943,8 @@ def emit_c(mod, subs_c, skipped, called, sources):
                 o.append("    %s %s;" % (ct, name))
         o.append("};")
     ctxn = Ctx(set())
-    for name, ct, init in mod.params:
-        o.append("static const %s %s = %s;" % (ct, ctxn.cname(name), init))
+    for name, ct, init in mod.params:  # initialised at load time in declaration order (initialisers may call sqrt)
+        o.append("static %s %s;" % (ct, ctxn.cname(name)))
     for name, ct, lo, vals in mod.parrays:
         o.append("static const %s %s_[] = {%s};" % (ct, name, ", ".join(vals)))
         o.append("#define %s(i) %s_[(i) - (%s)]" % (name, name, lo))
@@ -922,6 +956,10 @@ def emit_c(mod, subs_c, skipped, called, sources):
         o.append("static %s *%s_; static ref_array_desc %s_d = {\"%s\"};" % (ct, name, name, name))
         idx = ", ".join("ijk"[:rank])
         o.append("#define %s(%s) %s_[REF_IDX%d(%s, %s)]" % (name, idx, name, rank, name, idx))
+    o.append("__attribute__((constructor)) static void ref_init_parameters(void) {")
+    for name, ct, init in mod.params:
+        o.append("    %s = %s;" % (ctxn.cname(name), init))
+    o.append("}")
     # prototypes
     for head, body, argt in subs_c.values():
         o.append(head + ";")

@@ -50,8 +50,9 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
 __device__ __forceinline__ void alter_at(const Dev &P, int n) {
     const int c = P.fluid_cell[n];
     if (!(P.c_norm[c] > 1e-6)) return;
-    const double nwx = P.fluid_nw[5 * n + 0], nwy = P.fluid_nw[5 * n + 1], nwz = P.fluid_nw[5 * n + 2];
-    const double tcos = P.fluid_nw[5 * n + 3], tsin = P.fluid_nw[5 * n + 4];
+    const size_t nf = (size_t)P.num_fluid;
+    const double nwx = P.fluid_nw[n], nwy = P.fluid_nw[nf + n], nwz = P.fluid_nw[2 * nf + n];
+    const double tcos = P.fluid_nw[3 * nf + n], tsin = P.fluid_nw[4 * nf + n];
     const double x0 = P.cn_x[c], y0 = P.cn_y[c], z0 = P.cn_z[c];
     const double t1 = nwx * x0 + nwy * y0 + nwz * z0;
     const double t2 = 1.0 / sqrt(1 - t1 * t1);
@@ -73,11 +74,11 @@ __device__ __forceinline__ void alter_at(const Dev &P, int n) {
 }
 
 // K6: normal on solid boundary nodes inside the 0..n+1 box (MP/Phase_gradient.F90:88-109)
-__device__ __forceinline__ void cn_solid_at(const Dev &P, int n) {
+__device__ __forceinline__ void cn_solid_at(const Dev &P, int n, bool lazy = true) {
     const unsigned m = P.solid_mask[n];
     if (!(m & 0x80000000u)) return;
     const int c = P.solid_cell[n];
-    if (P.sparse) {
+    if (P.sparse && lazy) {
         // lazy path: if no listed fluid neighbour carries an interface (c_norm == 0 => n == 0) the result is exactly 0
         bool any = false;
 #pragma unroll
@@ -374,11 +375,13 @@ template <int K>
 __global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
     if (!P.tcount[2]) return;
     const int count = (K == 3 || K == 6) ? P.num_solid : (K == 4 ? P.nG : P.num_fluid);
+    // K6: the 18 extra |grad phi| reads of the lazy path only pay while a good part of the lattice has no interface
+    const bool lazy = (long long)P.tcount[0] * 2 < (long long)P.ntiles;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         if (K == 3) phi_solid_at(P, e);
-        else if (K == 4) gradient_at<true>(P, P.gcell[e]);
+        else if (K == 4) gradient_at<true>(P, P.gcell_r[e]);
         else if (K == 5) alter_at(P, e);
-        else cn_solid_at(P, e);
+        else cn_solid_at(P, e, lazy);
     }
 }
 
@@ -410,6 +413,11 @@ __global__ void __launch_bounds__(256) k_gradient_pack(const Dev P, int all) {
     }
 }
 
+// MEASURED AND REJECTED (r02_m4, C3 with random phi): the same with the normals staged through shared memory tile by
+// tile (128 threads per 8x4x4 tile, 10x6x6 halo box per component, two barriers): 5.6 ms against 2.6 ms for the gathers
+// above -- an 8x4x4 tile holds only ~46 fluid nodes, so most lanes idle through the stencil phase and every tile pays
+// four dependent memory round trips plus the barriers; the gathers of the list version run with full warps and hit L1 /
+// L2.  Same finding as for K4 in round 1 (k_gradient_tiles).
 void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st) {
     const Dev &P = c->d;
     if (!P.multiphase || !P.sparse || P.nA <= 0) return;

@@ -554,6 +554,10 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
                 if (W(i, j, k) != 1) gcell[n++] = g.cell(i, j, k);
     }
     d.nG = (int)nG;
+    if (d.use_tiles && nG > 0) {  // flat sweeps (most tiles active) keep the raster order
+        if (dev_alloc(ctx, &d.gcell_r, gcell.size(), false)) return MFLBM_ERR_CUDA;
+        CU(cudaMemcpy(d.gcell_r, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (d.use_tiles && nG > 0) {  // tile-driven gradient chain: gcell grouped by tile (raster order inside a tile)
         std::vector<int> tile((size_t)nG), order, start;
 #pragma omp parallel for schedule(static)
@@ -666,7 +670,10 @@ static int ensure_macro(mflbm_ctx *ctx) {
 static int ensure_phi_old(mflbm_ctx *ctx) {
     Dev &d = ctx->d;
     if (d.phi_old) return 0;
-    if (dev_alloc(ctx, &d.phi_old, d.g.ntot)) return MFLBM_ERR_CUDA;
+    if (dev_alloc(ctx, &d.phi_old, d.g.ntot, false)) return MFLBM_ERR_CUDA;
+    // never uploaded: start from the current phase field, like the reference seeds phi_old = phi when
+    // steady_state_option == 2 (MP/Init_multiphase.F90:341-347), so that the first d_phi_max is a real change
+    CU(cudaMemcpyAsync(d.phi_old, d.phi, (size_t)d.g.ntot * sizeof(double), cudaMemcpyDeviceToDevice, ctx->s_main));
     return 0;
 }
 
@@ -786,9 +793,10 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             if (s.ix < -1 || s.ix > g.nx + 2 || s.iy < -1 || s.iy > g.ny + 2 || s.iz < -1 || s.iz > nz + 2)
                 return fail(ctx, MFLBM_ERR_ARG, "fluid boundary node outside the 2-ghost-layer box");
             cell[n] = g.cell(s.ix, s.iy, s.iz);
-            nw[5 * n + 0] = s.nwx; nw[5 * n + 1] = s.nwy; nw[5 * n + 2] = s.nwz;
-            nw[5 * n + 3] = cos(s.theta);  // dcos/dsin of MP/Phase_gradient.F90:238-242, evaluated once by the host libm
-            nw[5 * n + 4] = sin(s.theta);
+            const size_t nf = (size_t)d.num_fluid;
+            nw[0 * nf + n] = s.nwx; nw[1 * nf + n] = s.nwy; nw[2 * nf + n] = s.nwz;
+            nw[3 * nf + n] = cos(s.theta);  // dcos/dsin of MP/Phase_gradient.F90:238-242, evaluated once by the host libm
+            nw[4 * nf + n] = sin(s.theta);
         }
         if (d.tcls[0]) {
             std::vector<int> tile(d.num_fluid), order, start;
@@ -798,7 +806,7 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             std::vector<double> nw2((size_t)5 * d.num_fluid);
             for (int n = 0; n < d.num_fluid; n++) {
                 cell2[n] = cell[order[n]];
-                for (int m = 0; m < 5; m++) nw2[(size_t)5 * n + m] = nw[(size_t)5 * order[n] + m];
+                for (int m = 0; m < 5; m++) nw2[(size_t)m * d.num_fluid + n] = nw[(size_t)m * d.num_fluid + order[n]];
             }
             cell.swap(cell2); nw.swap(nw2);
             CU(cudaMemcpy(d.tf_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1085,6 +1093,7 @@ static int fetch_red(mflbm_ctx *ctx, int n) {
 
 extern "C" int mflbm_monitor(mflbm_ctx *ctx, double *tk, int tk_len) {
     if (!ctx || !tk) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
     const int nz = ctx->cfg.nz;
     const bool mp = ctx->d.multiphase;
     const int need = mp ? 7 * nz + 3 : 2 * nz + 1;
@@ -1150,6 +1159,7 @@ extern "C" int mflbm_monitor_breakthrough(mflbm_ctx *ctx, int32_t *count) {
 
 extern "C" int mflbm_monitor_steady_phasefield(mflbm_ctx *ctx, double *umax_sq, double *d_phi_max) {
     if (!ctx || !umax_sq || !d_phi_max) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
     if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
     if (ensure_phi_old(ctx)) return MFLBM_ERR_CUDA;
     if (ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, ctx->s_main);
@@ -1170,6 +1180,7 @@ extern "C" int mflbm_monitor_steady_phasefield(mflbm_ctx *ctx, double *umax_sq, 
 extern "C" int mflbm_monitor_steady_capillarypressure(mflbm_ctx *ctx, double *umax_sq, double *pre_w, double *pre_nw,
                                                       int32_t *i_w, int32_t *i_nw) {
     if (!ctx || !umax_sq || !pre_w || !pre_nw || !i_w || !i_nw) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
     if (!ctx->d.multiphase) return fail(ctx, MFLBM_ERR_STATE, "multiphase only");
     int rc = mflbm_compute_macro_vars(ctx);
     if (rc) return rc;
@@ -1222,12 +1233,14 @@ extern "C" int mflbm_sync(mflbm_ctx *ctx) {
 
 extern "C" int mflbm_timer_start(mflbm_ctx *ctx) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev_t0, ctx->s_main));
     return MFLBM_OK;
 }
 
 extern "C" int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms) {
     if (!ctx || !elapsed_ms) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev_t1, ctx->s_main));
     CU(cudaEventSynchronize(ctx->ev_t1));
     float ms = 0;
@@ -1238,6 +1251,7 @@ extern "C" int mflbm_timer_stop(mflbm_ctx *ctx, double *elapsed_ms) {
 
 extern "C" int mflbm_profile(mflbm_ctx *ctx, int enable) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
     if (prof_flush(ctx)) return MFLBM_ERR_CUDA;
     ctx->prof = enable != 0;
     return MFLBM_OK;
@@ -1245,6 +1259,7 @@ extern "C" int mflbm_profile(mflbm_ctx *ctx, int enable) {
 
 extern "C" int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long *collide_launches) {
     if (!ctx || !collide_ms || !collide_launches) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
     if (prof_flush(ctx)) return MFLBM_ERR_CUDA;
     *collide_ms = ctx->prof_ms;
     *collide_launches = ctx->prof_launches;

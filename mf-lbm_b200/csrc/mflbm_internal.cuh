@@ -100,7 +100,7 @@ struct Dev {
     double *solid_law;     // la_weight
     int num_solid;
     int *fluid_cell;
-    double *fluid_nw;  // 5 doubles per node: nwx,nwy,nwz,cos(theta),sin(theta)
+    double *fluid_nw;  // structure of arrays [5][num_fluid]: nwx, nwy, nwz, cos(theta), sin(theta)
     int num_fluid;
     // sparse storage of the populations (DESIGN.md "Sparse population storage"): the 38 PDF arrays hold only
     // ACTIVE nodes = fluid nodes of 1..n (A, processed by the collision kernel, raster order k,j,i) followed by
@@ -125,7 +125,9 @@ struct Dev {
     int pf_dist;      // L2 software-prefetch distance of the odd step in nodes (0 = off)
     int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
-    int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated
+    int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated (grouped by tile
+                      // when use_tiles, raster order otherwise)
+    int *gcell_r;     // the same cells in raster order (k, j, i): the flat K4 sweep reads whole rows with it (use_tiles only)
     int nG;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
     // sparse multiphase layout: what the collision kernel needs of the colour gradient, PACKED by active index n so that a

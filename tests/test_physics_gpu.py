@@ -82,11 +82,6 @@ def test_laplace_law_static_droplet(layout):
     ctx.close()
 
 
-EXTRA = pytest.mark.skipif(__import__("os").environ.get("MFLBM_EXTRA_GPU_TESTS") != "1",
-                           reason="written after the round's GPU budget was spent: opt in with MFLBM_EXTRA_GPU_TESTS=1")
-
-
-@EXTRA
 @pytest.mark.parametrize("theta", [60.0, 120.0])
 def test_capillary_tube_young_laplace_with_contact_angle(theta):
     """GPU twin of tests/test_oracle.py::test_capillary_tube_young_laplace_with_contact_angle (wetting model end to end):

@@ -99,6 +99,19 @@ module mflbm_c
             type(c_ptr), value :: ctx
             type(mflbm_arrays), intent(in) :: host
         end function
+        integer(c_int) function mflbm_checkpoint_begin(ctx) bind(c, name="mflbm_checkpoint_begin")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx          ! returns 0: device snapshot taken, the step loop may go on; 1: context frozen
+        end function
+        integer(c_int) function mflbm_checkpoint_fetch(ctx, host) bind(c, name="mflbm_checkpoint_fetch")
+            import :: c_int, c_ptr, mflbm_arrays
+            type(c_ptr), value :: ctx
+            type(mflbm_arrays), intent(in) :: host
+        end function
+        integer(c_int) function mflbm_checkpoint_end(ctx) bind(c, name="mflbm_checkpoint_end")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+        end function
         integer(c_int) function mflbm_create(cfg, ctx) bind(c, name="mflbm_create")
             import :: c_int, c_ptr, mflbm_config
             type(mflbm_config), intent(in) :: cfg
@@ -301,6 +314,22 @@ contains
         type(mflbm_arrays) :: h
         call mflbm_fill_arrays(h, .false.)
         call mflbm_check(mflbm_download(mflbm_handle, h), 'mflbm_download(checkpoint)')
+    end subroutine
+
+    ! Staged variant of the same update (MP/IO_multiphase.F90:572-575): call mflbm_checkpoint_stage() at the step whose
+    ! state is to be saved (it returns at once when the device snapshot fits; the step loop goes on), and
+    ! mflbm_checkpoint_collect() right before save_checkpoint writes the arrays: the device-to-host copies run on a copy
+    ! stream and overlap the steps queued in between.  ntime+1 in the file header is the step of the stage call.
+    subroutine mflbm_checkpoint_stage()
+        integer(c_int) :: rc
+        rc = mflbm_checkpoint_begin(mflbm_handle)
+        if (rc < 0) call mflbm_check(rc, 'mflbm_checkpoint_begin')
+    end subroutine
+    subroutine mflbm_checkpoint_collect()
+        type(mflbm_arrays) :: h
+        call mflbm_fill_arrays(h, .false.)
+        call mflbm_check(mflbm_checkpoint_fetch(mflbm_handle, h), 'mflbm_checkpoint_fetch')
+        call mflbm_check(mflbm_checkpoint_end(mflbm_handle), 'mflbm_checkpoint_end')
     end subroutine
 
     ! replaces "!$acc update host(u,v,w,phi,rho)" after compute_macro_vars (MP/IO_multiphase.F90:686,792,857)

@@ -173,6 +173,27 @@ int mflbm_nccl_unique_id(unsigned char id[128]);
 int mflbm_output_begin(mflbm_ctx *ctx, int what);
 int mflbm_output_end(mflbm_ctx *ctx, const mflbm_arrays *host);
 
+/* ---- checkpoint staging (second half) -------------------------------------------------------
+ * save_checkpoint (MP/IO_multiphase.F90:562-642) does `!$acc update host(f0..f18, g0..g18, phi [, *_convec_bc])` and
+ * writes the per-rank stream file while the device waits; initialization_old_multi (MP/Init_multiphase.F90:477-557)
+ * reads the same arrays back (restart = mflbm_upload of them + mflbm_color_gradient, MP/Main_multiphase.F90:120).
+ *   mflbm_checkpoint_begin  freezes the state of the current step: when free device memory allows, a device-side snapshot
+ *                           of the populations (in the device layout), phi and the convective-outlet state is taken with
+ *                           stream-ordered copies and the step loop may go on at once (returns MFLBM_CKPT_STAGED = 0);
+ *                           otherwise nothing is copied and the context is frozen -- mflbm_step / mflbm_run are refused
+ *                           until mflbm_checkpoint_end (returns MFLBM_CKPT_DIRECT = 1).
+ *   mflbm_checkpoint_fetch  fills whichever of host->f[q], g[q], phi, f_convec_bc, g_convec_bc, phi_convec_bc are non-null
+ *                           with the frozen state, in the reference's extents (ghost layers included), on a copy stream
+ *                           that overlaps steps already queued; may be called repeatedly (one array at a time keeps the
+ *                           host footprint at one array, the way save_checkpoint writes them).  Entries of a population
+ *                           array that are dead storage in the sparse layout keep the caller's values, like mflbm_download.
+ *   mflbm_checkpoint_end    releases the snapshot / unfreezes the context. */
+#define MFLBM_CKPT_STAGED 0
+#define MFLBM_CKPT_DIRECT 1
+int mflbm_checkpoint_begin(mflbm_ctx *ctx);
+int mflbm_checkpoint_fetch(mflbm_ctx *ctx, const mflbm_arrays *host);
+int mflbm_checkpoint_end(mflbm_ctx *ctx);
+
 /* ---- geometry preprocessing on the device -------------------------------------------------
  * Replaces geometry_preprocessing_new (MP/Geometry_preprocessing.F90:9-512), called from set_walls / the main
  * program before initialization (MP/Main_multiphase.F90:98): classification of the wall array into solid / fluid

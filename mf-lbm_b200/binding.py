@@ -50,7 +50,7 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
            "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
            "mflbm_tile_stats", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
-           "mflbm_output_begin", "mflbm_output_end")
+           "mflbm_output_begin", "mflbm_output_end", "mflbm_checkpoint_begin", "mflbm_checkpoint_fetch", "mflbm_checkpoint_end")
 
 
 class GeometryConfig(C.Structure):
@@ -119,6 +119,9 @@ def load(strict=False):
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.mflbm_output_begin.argtypes = [vp, C.c_int]
     lib.mflbm_output_end.argtypes = [vp, C.POINTER(Arrays)]
+    lib.mflbm_checkpoint_begin.argtypes = [vp]
+    lib.mflbm_checkpoint_fetch.argtypes = [vp, C.POINTER(Arrays)]
+    lib.mflbm_checkpoint_end.argtypes = [vp]
     lib.mflbm_geometry_free.argtypes = [vp]
     lib.mflbm_geometry_free.restype = None
     lib.mflbm_geometry_last_error.restype = C.c_char_p
@@ -297,6 +300,34 @@ class Context:
         a = self._arrays(out, keep)
         self._chk(self.lib.mflbm_output_end(self.h, C.byref(a)), "mflbm_output_end")
         return out
+
+    CKPT_NAMES = ("f", "g", "phi", "f_convec_bc", "g_convec_bc", "phi_convec_bc")
+
+    def checkpoint_begin(self):
+        """freeze the state of the current step; returns 0 (device snapshot, stepping may go on) or 1 (context frozen)"""
+        rc = self.lib.mflbm_checkpoint_begin(self.h)
+        if rc < 0:
+            self._chk(rc, "mflbm_checkpoint_begin")
+        return rc
+
+    def checkpoint_fetch(self, *names, into=None):
+        """the frozen state of the named arrays in the reference's host layout ({name: ndarray}, 'f'/'g' lists of 19);
+        `into` = arrays to fill instead of fresh zero arrays (dead entries of the sparse layout keep their values)"""
+        out = into if into is not None else {}
+        for n in names:
+            if n in out:
+                continue
+            if n in ("f", "g"):
+                out[n] = [np.zeros(field_shape("f", self.nx, self.ny, self.nz), order="F") for _ in range(19)]
+            else:
+                out[n] = np.zeros(field_shape(n, self.nx, self.ny, self.nz), order="F")
+        keep = []
+        a = self._arrays({n: out[n] for n in names}, keep)
+        self._chk(self.lib.mflbm_checkpoint_fetch(self.h, C.byref(a)), "mflbm_checkpoint_fetch")
+        return out
+
+    def checkpoint_end(self):
+        self._chk(self.lib.mflbm_checkpoint_end(self.h), "mflbm_checkpoint_end")
 
     def monitor(self):
         """Device part of monitor: returns the reference's tk buffer split into named profiles."""

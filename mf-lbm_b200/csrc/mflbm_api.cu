@@ -156,6 +156,10 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->prof_ms = 0;
     ctx->prof_launches = 0;
     ctx->halo_buf[0] = ctx->halo_buf[1] = ctx->halo_buf[2] = ctx->halo_buf[3] = nullptr;
+    ctx->ckpt_mode = 0;
+    ctx->ev_ckpt = nullptr;
+    for (int q = 0; q < 19; q++) ctx->ckpt_f[q] = ctx->ckpt_g[q] = nullptr;
+    ctx->ckpt_phi = ctx->ckpt_fc = ctx->ckpt_gc = ctx->ckpt_pc = nullptr;
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
     ctx->red_dev = nullptr;
@@ -194,6 +198,7 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_out_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_ckpt, cudaEventDisableTiming));
         ctx->ev_phi_valid = false;
         Dev &d = ctx->d;
         d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
@@ -286,7 +291,16 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
         if (ctx->out_host[f]) cudaFreeHost(ctx->out_host[f]);
     }
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi, ctx->ev_out, ctx->ev_out_done};
+    {
+        double *ck[] = {ctx->ckpt_phi, ctx->ckpt_fc, ctx->ckpt_gc, ctx->ckpt_pc};
+        for (double *p : ck)
+            if (p) cudaFree(p);
+        for (int q = 0; q < 19; q++) {
+            if (ctx->ckpt_f[q]) cudaFree(ctx->ckpt_f[q]);
+            if (ctx->ckpt_g[q]) cudaFree(ctx->ckpt_g[q]);
+        }
+    }
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi, ctx->ev_out, ctx->ev_out_done, ctx->ev_ckpt};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     delete ctx;
@@ -677,20 +691,21 @@ static int ensure_phi_old(mflbm_ctx *ctx) {
     return 0;
 }
 
-// one field: host (ghost width o, nplanes planes starting at grid plane kbase) <-> device grid
-static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, int kbase, bool up) {
+// one field: host (ghost width o, nplanes planes starting at grid plane kbase) <-> device grid, on stream st
+static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, int kbase, bool up, cudaStream_t st = nullptr) {
     if (!host || !dev) return 0;
+    if (!st) st = ctx->s_main;
     const Grid &g = ctx->d.g;
     const size_t n = (size_t)(g.nx + 2 * o) * (g.ny + 2 * o) * nplanes;
     if (ensure_stage(ctx, n * sizeof(double))) return MFLBM_ERR_CUDA;
     if (up) {
-        CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
-        launch_repack(ctx, ctx->s_main, dev, ctx->stage, o, nplanes, kbase, true);
-        CU(cudaStreamSynchronize(ctx->s_main));
+        CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        launch_repack(ctx, st, dev, ctx->stage, o, nplanes, kbase, true);
+        CU(cudaStreamSynchronize(st));
     } else {
-        launch_repack(ctx, ctx->s_main, dev, ctx->stage, o, nplanes, kbase, false);
-        CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
-        CU(cudaStreamSynchronize(ctx->s_main));
+        launch_repack(ctx, st, dev, ctx->stage, o, nplanes, kbase, false);
+        CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
     }
     return 0;
 }
@@ -698,17 +713,18 @@ static int xfer(mflbm_ctx *ctx, double *dev, double *host, int o, int nplanes, i
 // one population array: caller's (0:nx+1,0:ny+1,0:nz+1) array <-> device (dense grid or active-node list).
 // Sparse download overwrites only the active entries of the caller's array: all other entries are never
 // touched by the reference either (they keep the values the caller's array already has).
-static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up, int q) {
+static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up, int q, cudaStream_t st = nullptr) {
     if (!host) return 0;
     if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "populations uploaded before the wall array");
+    if (!st) st = ctx->s_main;
     const Grid &g = ctx->d.g;
-    if (!ctx->d.sparse) return xfer(ctx, dev, host, 1, g.nz + 2, 0, up);
+    if (!ctx->d.sparse) return xfer(ctx, dev, host, 1, g.nz + 2, 0, up, st);
     const size_t n = (size_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
     if (ensure_stage(ctx, n * sizeof(double))) return MFLBM_ERR_CUDA;
-    CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_main));
-    launch_repack_sparse(ctx, ctx->s_main, dev, ctx->stage, up, q);
-    if (!up) CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
-    CU(cudaStreamSynchronize(ctx->s_main));
+    CU(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_repack_sparse(ctx, st, dev, ctx->stage, up, q);
+    if (!up) CU(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -963,6 +979,7 @@ static int collide_timed(mflbm_ctx *ctx, cudaStream_t s, bool odd, int k0, int k
 static int step_impl(mflbm_ctx *ctx, int ntime) {
     const mflbm_config &cfg = ctx->cfg;
     if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_step before mflbm_upload");
+    if (ctx->ckpt_mode == 2) return fail(ctx, MFLBM_ERR_STATE, "a checkpoint without device snapshot is pending: call mflbm_checkpoint_end first");
     const int nz = cfg.nz;
     const bool odd = (ntime % 2) != 0;
     cudaStream_t s = ctx->s_main;
@@ -1082,6 +1099,104 @@ extern "C" int mflbm_output_end(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (have && dst[f]) memcpy(dst[f], ctx->out_host[f], ctx->out_elems[f] * sizeof(double));
     }
     ctx->out_pending = 0;
+    return MFLBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// checkpoint staging (include/mflbm.h "checkpoint staging")
+// ---------------------------------------------------------------------------------------------------
+static size_t pdf_elems(const Dev &d, int q) {
+    return d.sparse ? (size_t)d.nAct + 64 + (size_t)d.nlink[OPC(q)] : (size_t)d.g.ntot;
+}
+
+static void ckpt_release(mflbm_ctx *ctx, cudaStream_t st) {
+    double **one[] = {&ctx->ckpt_phi, &ctx->ckpt_fc, &ctx->ckpt_gc, &ctx->ckpt_pc};
+    for (double **p : one)
+        if (*p) { cudaFreeAsync(*p, st); *p = nullptr; }
+    for (int q = 0; q < 19; q++) {
+        if (ctx->ckpt_f[q]) { cudaFreeAsync(ctx->ckpt_f[q], st); ctx->ckpt_f[q] = nullptr; }
+        if (ctx->ckpt_g[q]) { cudaFreeAsync(ctx->ckpt_g[q], st); ctx->ckpt_g[q] = nullptr; }
+    }
+}
+
+extern "C" int mflbm_checkpoint_begin(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_checkpoint_begin before mflbm_upload");
+    if (ctx->ckpt_mode) return fail(ctx, MFLBM_ERR_STATE, "a checkpoint is already pending: call mflbm_checkpoint_end first");
+    Dev &d = ctx->d;
+    cudaStream_t s = ctx->s_main;
+    if (d.multiphase && ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, s);  // the reference's phi on every listed solid node
+    const size_t plane = (size_t)d.g.sxy + 32;
+    size_t need = 0;
+    for (int q = 0; q < 19; q++) need += pdf_elems(d, q) * (d.multiphase ? 2 : 1);
+    need += (d.multiphase ? (size_t)d.g.ntot + 20 * plane : 0) + 19 * plane;
+    need *= sizeof(double);
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    const char *force = getenv("MFLBM_CKPT_DIRECT");  // developer / test switch: behave as if the snapshot did not fit
+    bool staged = fr > need + ((size_t)1 << 30) && !(force && atoi(force));
+    if (staged) {
+        auto snap = [&](double **dst, const double *src, size_t n) -> bool {
+            if (cudaMallocAsync((void **)dst, n * sizeof(double), s) != cudaSuccess) { *dst = nullptr; return false; }
+            return cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, s) == cudaSuccess;
+        };
+        bool ok = true;
+        for (int q = 0; q < 19 && ok; q++) {
+            ok = snap(&ctx->ckpt_f[q], d.f[q], pdf_elems(d, q));
+            if (ok && d.multiphase) ok = snap(&ctx->ckpt_g[q], d.gg[q], pdf_elems(d, q));
+        }
+        if (ok) ok = snap(&ctx->ckpt_fc, d.f_convec, 19 * plane);
+        if (ok && d.multiphase)
+            ok = snap(&ctx->ckpt_phi, d.phi, (size_t)d.g.ntot) && snap(&ctx->ckpt_gc, d.g_convec, 19 * plane) && snap(&ctx->ckpt_pc, d.phi_convec, plane);
+        if (!ok) {  // allocation failed after all: fall back to the frozen-context mode
+            cudaGetLastError();
+            ckpt_release(ctx, s);
+            staged = false;
+        }
+    }
+    if (staged) {
+        CU(cudaEventRecord(ctx->ev_ckpt, s));
+        ctx->ckpt_mode = 1;
+        return MFLBM_CKPT_STAGED;
+    }
+    ctx->ckpt_mode = 2;
+    return MFLBM_CKPT_DIRECT;
+}
+
+extern "C" int mflbm_checkpoint_fetch(mflbm_ctx *ctx, const mflbm_arrays *h) {
+    if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->ckpt_mode) return fail(ctx, MFLBM_ERR_STATE, "no checkpoint pending");
+    Dev &d = ctx->d;
+    const bool staged = ctx->ckpt_mode == 1;
+    // staged: copy stream, behind the snapshot, overlapping whatever steps are queued on the compute stream;
+    // direct: the live arrays of the (frozen) context on the compute stream
+    cudaStream_t st = staged ? ctx->s_copy : ctx->s_main;
+    if (staged) CU(cudaStreamWaitEvent(st, ctx->ev_ckpt, 0));
+    else CU(cudaStreamSynchronize(ctx->s_main));
+    for (int q = 0; q < 19; q++) {
+        if (xfer_pdf(ctx, staged ? ctx->ckpt_f[q] : d.f[q], h->f[q], false, q, st)) return MFLBM_ERR_CUDA;
+        if (d.multiphase && xfer_pdf(ctx, staged ? ctx->ckpt_g[q] : d.gg[q], h->g[q], false, q, st)) return MFLBM_ERR_CUDA;
+    }
+    if (d.multiphase) {
+        if (xfer(ctx, staged ? ctx->ckpt_phi : d.phi, h->phi, 4, d.g.nz + 8, -3, false, st)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, staged ? ctx->ckpt_gc : d.g_convec, h->g_convec_bc, 1, 19, -3, false, st)) return MFLBM_ERR_CUDA;
+        if (xfer(ctx, staged ? ctx->ckpt_pc : d.phi_convec, h->phi_convec_bc, 1, 1, -3, false, st)) return MFLBM_ERR_CUDA;
+    }
+    if (xfer(ctx, staged ? ctx->ckpt_fc : d.f_convec, h->f_convec_bc, 1, 19, -3, false, st)) return MFLBM_ERR_CUDA;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_checkpoint_end(mflbm_ctx *ctx) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->ckpt_mode) return fail(ctx, MFLBM_ERR_STATE, "no checkpoint pending");
+    if (ctx->ckpt_mode == 1) {
+        CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_ckpt, 0));  // never release ahead of the snapshot copies
+        ckpt_release(ctx, ctx->s_copy);
+    }
+    ctx->ckpt_mode = 0;
     return MFLBM_OK;
 }
 

@@ -246,6 +246,10 @@ struct mflbm_ctx {
     double *out_dev[5], *out_host[5];  // phi, u, v, w, rho in the caller's Fortran layout
     size_t out_elems[5];
     int out_pending;                   // field mask of the staged output in flight (0: none)
+    // checkpoint staging (mflbm_checkpoint_begin / _fetch / _end)
+    int ckpt_mode;                     // 0 none, 1 staged (device snapshot in ckpt_*), 2 direct (context frozen)
+    double *ckpt_f[19], *ckpt_g[19], *ckpt_phi, *ckpt_fc, *ckpt_gc, *ckpt_pc;
+    cudaEvent_t ev_ckpt;
     std::vector<void *> allocs;
     long long bytes;
     long long adj_bytes;  // size of the compressed adjacency

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -857,6 +858,86 @@ bool Driver::upload(bool with_geometry) {
             }
     }
     return true;
+}
+
+// save_checkpoint (MP/IO_multiphase.F90:562-642 ; SP/IO.F90 likewise): the per-rank stream file
+//   int32 ntime+1, f64 force_z, f64 rho_in, f0..f18 [, g0..g18, phi] [, f_convec_bc [, g_convec_bc, phi_convec_bc]]
+// with every array in the reference's extents (ghost layers included), written one array at a time from the staged
+// device snapshot (mflbm_checkpoint_begin / _fetch / _end): the device-to-host copies overlap whatever steps the caller
+// queued after mflbm_checkpoint_begin, and the host never holds more than one array.
+bool Driver::save_checkpoint(const std::string &path, int ntime) {
+    FILE *fp = std::fopen(path.c_str(), "wb");
+    if (!fp) { error = "cannot open " + path; return false; }
+    bool ok = true;
+    auto fail_ = [&](const std::string &m) { error = m; ok = false; };
+    int rc = mflbm_checkpoint_begin(ctx);  // no-op error if the caller already staged it earlier
+    if (rc < 0 && std::string(mflbm_last_error(ctx)).find("already pending") == std::string::npos) fail_(mflbm_last_error(ctx));
+    const int32_t nt = ntime + 1;
+    if (ok && (std::fwrite(&nt, 4, 1, fp) != 1 || std::fwrite(&force_Z, 8, 1, fp) != 1 || std::fwrite(&rho_in, 8, 1, fp) != 1)) fail_("write error");
+    std::vector<double> tmp;
+    auto put = [&](size_t slot, size_t n) {
+        if (!ok) return;
+        tmp.assign(n, 0.0);  // dead entries of the sparse layout (never read by anyone) are written as zeros
+        mflbm_arrays a;
+        std::memset(&a, 0, sizeof a);
+        *(double **)((char *)&a + slot) = tmp.data();
+        if (mflbm_checkpoint_fetch(ctx, &a) != MFLBM_OK) return fail_(mflbm_last_error(ctx));
+        if (std::fwrite(tmp.data(), 8, n, fp) != n) fail_("write error");
+    };
+    const size_t n1 = (size_t)(nx + 2) * (ny + 2) * (nz + 2), n4 = (size_t)(nx + 8) * (ny + 8) * (nz + 8), np = (size_t)(nx + 2) * (ny + 2);
+    for (int q = 0; q < 19; q++) put(offsetof(mflbm_arrays, f) + q * sizeof(double *), n1);
+    if (c.multiphase) {
+        for (int q = 0; q < 19; q++) put(offsetof(mflbm_arrays, g) + q * sizeof(double *), n1);
+        put(offsetof(mflbm_arrays, phi), n4);
+    }
+    if (c.outlet_BC == 1) {
+        put(offsetof(mflbm_arrays, f_convec_bc), np * 19);
+        if (c.multiphase) {
+            put(offsetof(mflbm_arrays, g_convec_bc), np * 19);
+            put(offsetof(mflbm_arrays, phi_convec_bc), np);
+        }
+    }
+    if (mflbm_checkpoint_end(ctx) != MFLBM_OK && ok) fail_(mflbm_last_error(ctx));
+    std::fclose(fp);
+    return ok;
+}
+
+// initialization_old_multi (MP/Init_multiphase.F90:477-557): read the stream file back, one array at a time, straight
+// into the existing context; returns ntime0 (the step to continue with)
+bool Driver::initialization_old(const std::string &path, int *ntime0) {
+    FILE *fp = std::fopen(path.c_str(), "rb");
+    if (!fp) { error = "Checkpoint data not found! Exiting program!"; return false; }
+    bool ok = true;
+    auto fail_ = [&](const std::string &m) { error = m; ok = false; };
+    int32_t nt = 0;
+    if (std::fread(&nt, 4, 1, fp) != 1 || std::fread(&force_Z, 8, 1, fp) != 1 || std::fread(&rho_in, 8, 1, fp) != 1) fail_("short checkpoint file");
+    if (ok && (mflbm_set_parameter(ctx, "force_Z", force_Z) != MFLBM_OK || mflbm_set_parameter(ctx, "rho_in", rho_in) != MFLBM_OK)) fail_(mflbm_last_error(ctx));
+    std::vector<double> tmp;
+    auto get = [&](size_t slot, size_t n) {
+        if (!ok) return;
+        tmp.resize(n);
+        if (std::fread(tmp.data(), 8, n, fp) != n) return fail_("short checkpoint file");
+        mflbm_arrays a;
+        std::memset(&a, 0, sizeof a);
+        *(double **)((char *)&a + slot) = tmp.data();
+        if (mflbm_upload(ctx, &a) != MFLBM_OK) fail_(mflbm_last_error(ctx));
+    };
+    const size_t n1 = (size_t)(nx + 2) * (ny + 2) * (nz + 2), n4 = (size_t)(nx + 8) * (ny + 8) * (nz + 8), np = (size_t)(nx + 2) * (ny + 2);
+    for (int q = 0; q < 19; q++) get(offsetof(mflbm_arrays, f) + q * sizeof(double *), n1);
+    if (c.multiphase) {
+        for (int q = 0; q < 19; q++) get(offsetof(mflbm_arrays, g) + q * sizeof(double *), n1);
+        get(offsetof(mflbm_arrays, phi), n4);
+    }
+    if (c.outlet_BC == 1) {
+        get(offsetof(mflbm_arrays, f_convec_bc), np * 19);
+        if (c.multiphase) {
+            get(offsetof(mflbm_arrays, g_convec_bc), np * 19);
+            get(offsetof(mflbm_arrays, phi_convec_bc), np);
+        }
+    }
+    std::fclose(fp);
+    if (ok && ntime0) *ntime0 = nt;
+    return ok;
 }
 
 bool Driver::main_iteration_kernel(int ntime) {

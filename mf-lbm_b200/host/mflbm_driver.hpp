@@ -105,6 +105,8 @@ public:
     bool upload(bool with_geometry = true);
     void random_phase_field(unsigned long long seed);      // option 6 with a seeded, decomposition-independent draw
     bool reinitialize(int option, unsigned long long seed);  // new initial fluid distribution on the same geometry
+    bool save_checkpoint(const std::string &path, int ntime);        // MP/IO_multiphase.F90:562-642 (staged, array by array)
+    bool initialization_old(const std::string &path, int *ntime0);   // MP/Init_multiphase.F90:477-557
     bool main_iteration_kernel(int ntime);          // MP/Main_multiphase.F90:341-486 -> mflbm_step
     bool color_gradient();                          // MP/Phase_gradient.F90:5 -> mflbm_color_gradient
     bool monitor(int ntime, MonitorResult *out, const std::string &outdir);  // MP/Monitor.F90:5-277 (np==1 tail)

@@ -73,6 +73,8 @@ int mfd_create_context(void *h, int device, int use_nccl, const unsigned char *n
     return ((Driver *)h)->create_context(device, use_nccl, nccl_id, kernel_variant) ? 0 : -1;
 }
 int mfd_upload(void *h) { return ((Driver *)h)->upload() ? 0 : -1; }
+int mfd_save_checkpoint(void *h, const char *path, int ntime) { return ((Driver *)h)->save_checkpoint(path, ntime) ? 0 : -1; }
+int mfd_initialization_old(void *h, const char *path, int *ntime0) { return ((Driver *)h)->initialization_old(path, ntime0) ? 0 : -1; }
 int mfd_reinitialize(void *h, int option, unsigned long long seed) { return ((Driver *)h)->reinitialize(option, seed) ? 0 : -1; }
 void *mfd_ctx(void *h) { return ((Driver *)h)->ctx; }
 int mfd_main_iteration_kernel(void *h, int ntime) { return ((Driver *)h)->main_iteration_kernel(ntime) ? 0 : -1; }

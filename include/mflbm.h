@@ -56,7 +56,8 @@ typedef struct {
     int32_t nx, ny, nz;             /* local slab (MP/Module.F90:80) */
     int32_t nxGlobal, nyGlobal, nzGlobal;
     int32_t idz, npz;               /* slab position; x,y undivided (MP/IO_multiphase.F90:495-498) */
-    int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference) */
+    int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference); jper = 1 is not
+                                       supported yet: mflbm_create returns MFLBM_ERR_ARG */
     int32_t domain_wall_status_z_min, domain_wall_status_z_max;
     int32_t inlet_BC, outlet_BC;    /* 1 velocity / convective, 2 Zou-He pressure */
     int32_t porous_plate_cmd, Z_porous_plate;
@@ -65,7 +66,9 @@ typedef struct {
     int32_t num_solid_boundary, num_fluid_boundary;
     int32_t device;                 /* CUDA ordinal; <0 = keep current (replaces setDevice, MP/Misc.F90:437) */
     int32_t use_nccl;               /* 1: z-halo exchange between ranks with ncclSend/ncclRecv */
-    int32_t kernel_variant;         /* 0 = default (fused), 1 = reference-order dataflow (debug/parity) */
+    int32_t kernel_variant;         /* population layout: 0 = auto (sparse active-node list when porosity <= 0.8, else dense),
+                                       1 = dense (the reference's direct addressing), 2 = sparse.  porous_plate_cmd != 0
+                                       always runs dense (the plate copies from arbitrary nodes).  Results are identical. */
     int32_t reserved_i[7];
     double la_nui1, la_nui2;        /* 1/nu1, 1/nu2 (MP/Init_multiphase.F90:120-121) */
     double gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;

@@ -99,6 +99,13 @@ __device__ __forceinline__ void node_update(const Dev &P, const int n, const int
                         if (MP) prefetch_l2(P.gg[OPC(d)] + pq);
                     }
                 }
+                if (PF == 2) {
+                    // metadata only: the adjacency records (five 128-byte lines per warp) and the cell list of the warp
+                    // pf_dist nodes ahead -- the two loads every other load of that warp depends on -- become L2 hits
+                    const int wn = min((n + P.pf_dist) >> 5, (P.nA - 1) >> 5);
+                    if (lane < 5) prefetch_l2(reinterpret_cast<const char *>(P.adj + (size_t)wn * MFLBM_ADJ_REC) + 128 * lane);
+                    if (lane == 5) prefetch_l2(P.cellA + min(n + P.pf_dist, P.nA - 1));
+                }
                 if (PF == 1) {
                     const int wn = min((n + P.pf_dist) >> 5, (P.nA - 1) >> 5);
                     if (lane < 5) prefetch_l2(reinterpret_cast<const char *>(P.adj + (size_t)wn * MFLBM_ADJ_REC) + 128 * lane);
@@ -224,7 +231,8 @@ static void launch_collide_t(mflbm_ctx *c, cudaStream_t st, bool odd, int k0, in
     }
     const bool pf = SPARSE && odd && P.pf_dist > 0;  // L2 software prefetch: a separate instantiation, no dead issue slots
     if (P.multiphase) {
-        if (pf) k_collide<true, true, SPARSE, SPARSE ? 1 : 0><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        if (pf && P.pf_mode == 2) k_collide<true, true, SPARSE, SPARSE ? 2 : 0><<<grid, block, 0, st>>>(P, k0, n0, n1);
+        else if (pf) k_collide<true, true, SPARSE, SPARSE ? 1 : 0><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else if (odd) k_collide<true, true, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
         else k_collide<true, false, SPARSE><<<grid, block, 0, st>>>(P, k0, n0, n1);
     } else {

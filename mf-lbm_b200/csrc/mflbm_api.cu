@@ -593,6 +593,8 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
         // more than the L2 hits return), so it is off there.  MFLBM_PF_DIST overrides.
         const char *e = getenv("MFLBM_PF_DIST");
         d.pf_dist = e ? atoi(e) : (d.multiphase ? 0 : 65536);
+        const char *m = getenv("MFLBM_PF_MODE");
+        d.pf_mode = m ? atoi(m) : 1;
     }
     if (dev_alloc(ctx, &d.cellA, (size_t)nAct + 32, false) || dev_alloc(ctx, &d.adj, adj.size(), false) ||
         dev_alloc(ctx, &d.adjfull, full.size(), false) || dev_alloc(ctx, &d.smap, (size_t)g.ntot, false))

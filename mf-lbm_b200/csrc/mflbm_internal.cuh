@@ -123,6 +123,7 @@ struct Dev {
     uint4 *adj;       // [ceil(nA/32)][37]
     int *adjfull;     // [rows][32]
     int pf_dist;      // L2 software-prefetch distance of the odd step in nodes (0 = off)
+    int pf_mode;      // 1: populations + metadata (singlephase default), 2: adjacency records + cell list only
     int nlink[19];    // number of link slots of direction d (stored behind the node entries of population array opc(d))
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated (grouped by tile

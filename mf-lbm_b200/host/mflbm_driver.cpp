@@ -302,14 +302,19 @@ void Driver::modify_geometry() {  // MP/Misc.F90:213-244
     const double r1 = 0.25 * nyG, r2 = nyG * 0.5;
     const int buffer = 10;
 #pragma omp parallel for
-    for (int k = std::max(1, wk0); k <= std::min(nzG, wk1); k++)
+    // every plane of the held window, the wrapped ghost planes of a z-periodic window included: they image the global plane
+    // kg, which the rank holding it modifies too (the reference modifies the whole global array before distributing it)
+    for (int kw = wk0; kw <= wk1; kw++) {
+        const int k = ((kw - 1) % nzG + nzG) % nzG + 1;
+        if (k != kw && c.kper != 1) continue;  // outside an open lattice: not a lattice plane
         for (int j = 1; j <= nyG; j++)
             for (int i = 1; i <= nxG; i++) {
                 const double dx = i - xc, dy = j - yc, dz = k - zc;
-                int8_t &w = walls_global[(size_t)(i - 1) + (size_t)nxG * ((size_t)(j - 1) + (size_t)nyG * (k - wk0))];
+                int8_t &w = walls_global[(size_t)(i - 1) + (size_t)nxG * ((size_t)(j - 1) + (size_t)nyG * (kw - wk0))];
                 if (dx * dx + dy * dy + dz * dz < r1 * r1) w = 1;
                 if (dx * dx + dy * dy > r2 * r2 && k > buffer && k < nzG - buffer + 1) w = 1;
             }
+    }
 }
 
 void Driver::set_walls() {  // MP/Misc.F90:6-210, pore_profile :298-365, transport_walls MP/Mpi_misc.F90:337-502

@@ -45,6 +45,16 @@ int mfd_set_walls_global(void *h, const int8_t *w, int nxs, int nys, int nzs) {
 // wrapped by the caller on a periodic one).  Lets each rank hold and preprocess only its own part of the geometry.
 int mfd_set_walls_window(void *h, const int8_t *w, int nplanes, int wk0) {
     Driver *d = (Driver *)h;
+    {   // same extent rule as mflbm_geometry_preprocess: the window reaches the lattice end or >= 10 planes beyond the slab
+        // (smoothing 4 + ISO8 2 + list ghosts 3, + the 2 ghost planes set_walls fills); a smaller one would be read out of bounds
+        const int nzG = d->c.nzGlobal, nz = nzG / (d->c.npz > 0 ? d->c.npz : 1);
+        const int ks0 = d->idz * nz + 1, ks1 = d->idz * nz + nz, wk1 = wk0 + nplanes - 1;
+        const bool lo_ok = wk0 <= ks0 - 10 || (d->c.kper == 0 && wk0 <= 1), hi_ok = wk1 >= ks1 + 10 || (d->c.kper == 0 && wk1 >= nzG);
+        if (!lo_ok || !hi_ok) {
+            d->error = "wall window too small: it must reach the lattice end or extend >= 10 planes beyond the slab";
+            return -1;
+        }
+    }
     const size_t n = (size_t)d->c.nxGlobal * d->c.nyGlobal * nplanes;
     d->walls_global.assign(w, w + n);
     d->wk0 = wk0;

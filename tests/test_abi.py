@@ -59,3 +59,23 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in txt.lower().replace("cpu oracle", "").replace("the oracle", ""), (dirpath, fn)
+
+
+def test_fortran_offset_table_is_current(tmp_path):
+    """fortran/mflbm_abi_offsets.txt (what a maintainer compares the type, bind(c) declarations with) is the output of
+    tools/gen_abi_offsets.c for the header as it is now, and the ctypes mirror agrees with it"""
+    import subprocess
+    exe = str(tmp_path / "gen")
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "gen_abi_offsets.c"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "fortran", "mflbm_abi_offsets.txt")).read()
+    import mflbm_b200 as M
+    table = {}
+    for line in out.splitlines()[1:]:
+        st, mem, off, size = line.split()
+        table[(st, mem)] = (off, int(size))
+    for name, typ in (("mflbm_config", M.Config), ("mflbm_arrays", M.Arrays), ("mflbm_geometry_config", M.GeometryConfig)):
+        assert table[(name, "(sizeof)")][1] == __import__("ctypes").sizeof(typ)
+        for fname, _ in typ._fields_:
+            if (name, fname) in table:
+                assert int(table[(name, fname)][0]) == getattr(typ, fname).offset, (name, fname)

@@ -124,6 +124,32 @@ def test_windowed_geometry_matches_whole_lattice(tmp_path):
 
 
 @pytest.mark.parametrize("kper", [0, 1])
+def test_windowed_modify_geometry_matches_whole_lattice(tmp_path, kper):
+    """modify_geometry_cmd = 1 on a z window: the tube + sphere is carved into every held plane, the wrapped ghost planes of a
+    z-periodic window included (the reference modifies the whole global array before distributing it, MP/Misc.F90:213-244),
+    so that walls and boundary-node lists agree across the periodic seam."""
+    nzG, npz = 96, 4
+    for idz in range(npz):
+        kw = dict(lattice_dimensions="24,24,%d" % nzG, MPI_process_num="1,1,%d" % npz, periodic_indicator="0,0,%d" % kper,
+                  excluded_layers="0,0", inlet_BC=0 if kper else 1, outlet_BC=0 if kper else 1, body_force_0="1d-5", modify_geometry_cmd=1)
+        ctl = M.write_control_file(str(tmp_path / "c.txt"), **kw)
+        k0, k1 = M.Driver.window_range(idz, npz, nzG, kper)
+        dw = M.Driver(ctl, idz=idz, walls_window=(np.zeros((24, 24, k1 - k0 + 1), np.int8), k0))
+        dw.setup()
+        o = make_oracle(nxG=24, nyG=24, nzG=nzG, npz=npz, idz=idz, kper=kper, n_exclude_inlet=0, n_exclude_outlet=0, force_z0=1e-5,
+                        inlet_BC=0 if kper else 1, outlet_BC=0 if kper else 1, modify_geometry_cmd=1)
+        assert np.array_equal(dw.walls, o.walls), (kper, idz)
+        _same_lists(dw, o)
+        dw.close()
+
+
+def test_too_small_wall_window_is_refused(tmp_path):
+    ctl = M.write_control_file(str(tmp_path / "c.txt"), lattice_dimensions="14,12,96", MPI_process_num="1,1,4")
+    with pytest.raises(M.MflbmError, match="wall window too small"):
+        M.Driver(ctl, idz=1, walls_window=(np.zeros((14, 12, 30), np.int8), 22))  # slab 25..48 needs planes 15..58
+
+
+@pytest.mark.parametrize("kper", [0, 1])
 def test_windowed_wall_file_read_equals_the_whole_file_path(tmp_path, kper):
     """every rank reads only the planes around its slab from the reference wall-array file (seek, no
     whole-lattice array, no broadcast) and ends up with exactly the local walls, pore counts and boundary-node lists that

@@ -294,6 +294,10 @@ contains
         h%g(11) = c_loc(g10); h%g(12) = c_loc(g11); h%g(13) = c_loc(g12); h%g(14) = c_loc(g13); h%g(15) = c_loc(g14)
         h%g(16) = c_loc(g15); h%g(17) = c_loc(g16); h%g(18) = c_loc(g17); h%g(19) = c_loc(g18)
         h%phi = c_loc(phi); h%phi_old = c_null_ptr
+        ! steady_state_option 2: phi_old (= phi after initialization_new_multi, MP/Init_multiphase.F90:341-347) goes up with
+        ! the rest, so that the first monitor_multiphase_steady_phasefield measures the change since the start like the
+        ! reference; without it the library seeds phi_old from phi at the first monitor call
+        if (with_geometry .and. steady_state_option == 2) h%phi_old = c_loc(phi_old)
         h%cn_x = c_null_ptr; h%cn_y = c_null_ptr; h%cn_z = c_null_ptr; h%c_norm = c_null_ptr; h%curv = c_null_ptr
         h%u = c_null_ptr; h%v = c_null_ptr; h%w = c_null_ptr; h%rho = c_null_ptr
         h%walls = c_null_ptr; h%w_in = c_null_ptr

@@ -114,6 +114,8 @@ def load(strict=False):
     lib.mflbm_launch_count.restype = C.c_longlong
     lib.mflbm_device_bytes.argtypes = [vp]
     lib.mflbm_device_bytes.restype = C.c_longlong
+    lib.mflbmx_spec_steps.argtypes = [vp]
+    lib.mflbmx_spec_steps.restype = C.c_longlong
     lib.mflbm_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte * 128)]
     lib.mflbm_geometry_preprocess.argtypes = [C.POINTER(GeometryConfig), C.c_void_p, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -401,3 +403,8 @@ class Context:
     @property
     def device_bytes(self):
         return self.lib.mflbm_device_bytes(self.h)
+
+    @property
+    def spec_steps(self):
+        """steps that ran with the speculative early gradient chain (DESIGN.md "Step schedule")"""
+        return self.lib.mflbmx_spec_steps(self.h)

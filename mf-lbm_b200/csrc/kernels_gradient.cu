@@ -2,6 +2,8 @@
 //
 // Replaces color_gradient (MP/Phase_gradient.F90:5-204) and alter_color_gradient_solid_surface
 // (MP/Phase_gradient.F90:210-265): five launches K3..K7 exactly like the reference's five loop nests.
+#include <algorithm>
+
 #include "gradient.cuh"
 
 namespace mflbm {
@@ -29,6 +31,8 @@ __device__ __forceinline__ void phi_solid_at(const Dev &P, int n) {
 // ever writes n at solid-boundary nodes (fully, after this kernel), so not touching solid nodes is unobservable.
 template <bool LAZY>
 __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
+    // (loading the 19 values as one pinned batch like curvature_at does -- Stencil19 -- was measured: flat K4 unchanged at
+    // 1.19 ms on C3 with random phi, the tile-driven K4 slower because of its 56 registers; r02_m6)
     const int sx = P.g.sx, sxy = P.g.sxy;
     const double *__restrict__ ph = P.phi;
     auto v = [&](int a, int b, int d) { return ph[c + a + sx * b + sxy * d]; };
@@ -49,8 +53,8 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
 // K5: geometric wetting (Akai et al. 2018), MP/Phase_gradient.F90:225-261; cos/sin(theta) precomputed on the host
 __device__ __forceinline__ void alter_at(const Dev &P, int n) {
     const int c = P.fluid_cell[n];
-    if (!(P.c_norm[c] > 1e-6)) return;
     const size_t nf = (size_t)P.num_fluid;
+    if (!(P.c_norm[c] > 1e-6)) return;
     const double nwx = P.fluid_nw[n], nwy = P.fluid_nw[nf + n], nwz = P.fluid_nw[2 * nf + n];
     const double tcos = P.fluid_nw[3 * nf + n], tsin = P.fluid_nw[4 * nf + n];
     const double x0 = P.cn_x[c], y0 = P.cn_y[c], z0 = P.cn_z[c];
@@ -226,10 +230,13 @@ __global__ void __launch_bounds__(128) k_tile_static(const Dev P, const unsigned
 // previous step's U.  Active tiles are appended to tact; every tile within one tile of an active tile is appended
 // (once, guarded by a per-step stamp) to tk3: K3 must refresh phi on every solid node an active evaluation can read.
 // Also clears the class buffer the next step will write.
-__global__ void k_tile_update(const Dev P, int cur, int stamp) {
+// tz_lo..tz_hi, inside: only the tiles whose layer tz lies inside (inside = 1) / outside (inside = 0) that range -- the two
+// halves of a speculative step (mflbm_api.cu step_impl); the whole lattice is (0, ntz - 1, 1).
+__global__ void k_tile_update(const Dev P, int cur, int stamp, int tz_lo, int tz_hi, int inside) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.ntiles) return;
     const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
+    if ((tz >= tz_lo && tz <= tz_hi) != (inside != 0)) return;
     unsigned U = 0;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = tz + dz;
@@ -252,6 +259,8 @@ __global__ void k_tile_update(const Dev P, int cur, int stamp) {
     P.tcls[cur ^ 1][t] = 0;
     if (quiet) return;
     P.tact[atomicAdd(&P.tcount[0], 1)] = t;
+    atomicMax(&P.tcount[5], P.ntz - tz);  // layer range of the active tiles (zero-initialised: min as ntz - tz, max as tz + 1)
+    atomicMax(&P.tcount[6], tz + 1);
     for (int dz = -1; dz <= 1; dz++) {
         const int z = tz + dz;
         if (z < 0 || z >= P.ntz) continue;
@@ -294,7 +303,7 @@ __device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int sta
 #define MFLBM_K4_ROW 24  // shared-memory row pitch in doubles (10 used): 8 mod 16 keeps half-warps conflict-free
 __global__ void __launch_bounds__(128) k_gradient_tiles(const Dev P, int stamp) {
     __shared__ double sphi[6 * 6 * MFLBM_K4_ROW];
-    if (P.tcount[2]) return;  // most tiles active: the flat kernels run instead
+    if (!P.tcount[3]) return;  // most tiles active: the flat kernels run instead
     const int count = P.tcount[0];
     const int sx = P.g.sx, sxy = P.g.sxy;
     const int tid = threadIdx.x;
@@ -340,13 +349,16 @@ __global__ void k_tile_all(const Dev P) {
         P.tcount[0] = P.ntiles;
         P.tcount[1] = P.ntiles;
         P.tcount[2] = 1;
+        P.tcount[3] = 0;
+        P.tcount[5] = P.ntz;
+        P.tcount[6] = P.ntz;
     }
 }
 
 // tile-driven launch shape: persistent blocks walk a tile list; the threads of a block share the entries of one tile
 template <int K>
-__global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp) {
-    if (P.tcount[2]) return;  // most tiles active: k_chain_flat<K> runs instead
+__global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp, int force) {
+    if (!force && !P.tcount[3]) return;  // most tiles active: k_chain_flat<K> runs instead (or nothing is left to do)
     const int *__restrict__ list = K == 3 ? P.tk3 : P.tact;
     const int count = P.tcount[K == 3 ? 1 : 0];
     const int *__restrict__ start = (K == 3 || K == 6) ? P.ts_start : (K == 4 ? P.tg_start : P.tf_start);
@@ -369,7 +381,17 @@ __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp) {
 // tile-driven); the flat kernels below then sweep the whole node lists with full warps.  Both shapes are always
 // launched, the one that is not selected returns at once (fixed grid-stride grids, so an idle launch costs microseconds).
 // Evaluating a quiet tile anyway is exact: it reproduces the zeros / the K3 means the skipped evaluation would give.
-__global__ void k_tile_mode(const Dev P) { P.tcount[2] = (long long)P.tcount[0] * 4 > (long long)P.ntiles ? 1 : 0; }
+// tcount[2] = 1: flat sweep (every warp then counts as active in the next collision), tcount[3] = 1: tile-driven pass.
+// spec = 1 (second half of a speculative step): tcount[4] holds the number of active tiles the early pass already
+// evaluated; nothing more runs unless the rest of the lattice turned out to hold active tiles too (a "miss"), in which
+// case the whole list is evaluated again -- the chain is idempotent (K4 rewrites what K5 alters).
+__global__ void k_tile_mode(const Dev P, int spec) {
+    const bool many = (long long)P.tcount[0] * 4 > (long long)P.ntiles;
+    const bool need = !spec || P.tcount[0] > P.tcount[4];
+    P.tcount[2] = (need && many) ? 1 : 0;
+    P.tcount[3] = (need && !many) ? 1 : 0;
+}
+__global__ void k_tile_mark(const Dev P) { P.tcount[4] = P.tcount[0]; }
 
 template <int K>
 __global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(256) k_gradient_pack(const Dev P, int all) {
     const int lane = threadIdx.x & 31;
     const int nW = (P.nA + 31) >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-    if (!all && P.use_tiles) all = P.tcount[2];
+    if (!all && P.use_tiles && P.tcount[2]) return;  // k_gradient_pack_all did it
     for (int w0 = gw * 32; w0 < nW; w0 += tw * 32) {
         unsigned m = 0xffffffffu;
         if (!all) m = __ballot_sync(0xffffffffu, w0 + lane < nW && P.wstamp[w0 + lane] == P.wq_stamp);
@@ -418,13 +440,64 @@ __global__ void __launch_bounds__(256) k_gradient_pack(const Dev P, int all) {
 // above -- an 8x4x4 tile holds only ~46 fluid nodes, so most lanes idle through the stencil phase and every tile pays
 // four dependent memory round trips plus the barriers; the gathers of the list version run with full warps and hit L1 /
 // L2.  Same finding as for K4 in round 1 (k_gradient_tiles).
+// Grid of a grid-stride kernel = exactly the blocks that are resident at once.  With more blocks than that, the first
+// resident set strides through the WHOLE list before the next set starts, i.e. the lattice is swept several times and
+// the stencil neighbourhoods fall out of L2 between the sweeps (measured, r02 ncu: k_gradient_pack with 4x oversubscribed
+// grid read 13.7 GB from DRAM for 4.5 GB of operands).
+template <typename K>
+static int resident_grid(K kernel, int block) {
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+// Every fluid node.  Resident blocks draw chunks of 256 consecutive nodes from a ticket counter, so the chunks in flight
+// always form one compact window of ~2 lattice planes and the three planes a node's stencil reads stay in L2 between
+// their uses, like with an ordinary one-block-per-chunk launch -- but a launch that has nothing to do (tile mode) costs a
+// few microseconds instead of one empty block per chunk (measured: 117 us on C3, 0.6 ns per block).  The grid-stride
+// scan above lets blocks drift apart over its ~170 iterations: 13.7 GB DRAM reads for 4.5 GB of operands on C3 with random
+// phi, every plane fetched three times (r02 ncu).  force = 0: runs only when the chain of this step swept every tile.
+__global__ void __launch_bounds__(256, 3) k_gradient_pack_all(const Dev P, int force) {
+    if (!force && !P.tcount[2]) return;
+    __shared__ int s_chunk;
+    const int nchunk = (P.nA + 255) >> 8;
+    for (;;) {
+        if (threadIdx.x == 0) s_chunk = atomicAdd(&P.tcount[8], 1);
+        __syncthreads();
+        const int chunk = s_chunk;
+        __syncthreads();
+        if (chunk >= nchunk) return;
+        const int n = (chunk << 8) + threadIdx.x;
+        if (n >= P.nA) continue;
+        const int c = P.cellA[n];
+        const double cnorm = P.c_norm[c];
+        double cnx = 0.0, cny = 0.0, cnz = 0.0, tmp = 0.0;
+        if (cnorm != 0.0) {
+            cnx = P.cn_x[c]; cny = P.cn_y[c]; cnz = P.cn_z[c];
+            tmp = 0.5 * P.gamma * curvature_at(P, c) * cnorm;
+        }
+        P.G[0][n] = cnx; P.G[1][n] = cny; P.G[2][n] = cnz; P.G[3][n] = tmp;
+    }
+}
+
 void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st) {
     const Dev &P = c->d;
     if (!P.multiphase || !P.sparse || P.nA <= 0) return;
     const int all = (!P.use_tiles || P.wq_all) ? 1 : 0;
+    static int cap = 0, cap_all = 0;
+    if (!cap) {
+        cap = resident_grid(k_gradient_pack, 256);
+        cap_all = resident_grid(k_gradient_pack_all, 256);
+    }
+    cudaMemsetAsync(P.tcount + 8, 0, sizeof(int), st);  // ticket counter
+    k_gradient_pack_all<<<std::min(cap_all, (P.nA + 255) / 256), 256, 0, st>>>(P, all);
+    c->launches++;
+    if (all) return;
     int nb = (P.nA + 255) / 256;
-    if (nb > 148 * 16) nb = 148 * 16;
-    k_gradient_pack<<<nb, 256, 0, st>>>(P, all);
+    if (nb > cap) nb = cap;
+    k_gradient_pack<<<nb, 256, 0, st>>>(P, 0);  // returns at once when tcount[2] is set
     c->launches++;
 }
 
@@ -477,15 +550,84 @@ void launch_phi_solid_refresh(mflbm_ctx *c, cudaStream_t st) {
 
 // stepping = true: called from mflbm_step right after the collision kernel, which recorded the phi classes of this
 // step; otherwise (explicit mflbm_color_gradient, e.g. before the first step) every tile is evaluated.
+// K3..K6: force = 1 runs the tile-driven kernels unconditionally over the lists as they are now (early half of a
+// speculative step), otherwise the gated tile-driven AND flat kernels (whichever k_tile_mode / k_tile_all selected)
+static void launch_chain_kernels(mflbm_ctx *c, cudaStream_t st, bool tiles, bool force) {
+    const Dev &P = c->d;
+    const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
+    static int fcap[4] = {0, 0, 0, 0};
+    if (!fcap[0]) {
+        fcap[0] = resident_grid(k_chain_flat<3>, 256); fcap[1] = resident_grid(k_chain_flat<4>, 256);
+        fcap[2] = resident_grid(k_chain_flat<5>, 256); fcap[3] = resident_grid(k_chain_flat<6>, 256);
+    }
+    const int f = force ? 1 : 0;
+    int n = 0;
+    // K4 (tile-driven) also stamps the warps of the active tiles (nG > 0 whenever there is a fluid node)
+    if (P.num_solid > 0) {
+        if (tiles) { k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0, f); n++; }
+        if (!force) { k_chain_flat<3><<<fcap[0], 256, 0, st>>>(P); n++; }
+    }
+    if (P.nG > 0) {
+        if (tiles) {
+            if (P.k4_smem && !force) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
+            else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, c->tile_stamp, f);
+            n++;
+        }
+        if (!force) { k_chain_flat<4><<<fcap[1], 256, 0, st>>>(P); n++; }
+    }
+    if (P.num_fluid > 0) {
+        if (tiles) { k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0, f); n++; }
+        if (!force) { k_chain_flat<5><<<fcap[2], 256, 0, st>>>(P); n++; }
+    }
+    if (P.num_solid > 0) {
+        if (tiles) { k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0, f); n++; }
+        if (!force) { k_chain_flat<6><<<fcap[3], 256, 0, st>>>(P); n++; }
+    }
+    c->launches += n;
+}
+
+// Speculative step, early half (stream st runs beside the collision of the far planes): tile update of the layers
+// tz_lo..tz_hi only and the chain K3..K6 over the active tiles found there.  Everything these kernels read -- phi and tile
+// classes of the layers tz_lo-2..tz_hi+2 -- has been written by the collision of the near planes already (step_impl).
+void launch_chain_early(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi) {
+    Dev &P = c->d;
+    const int nb = (P.ntiles + 127) / 128;
+    // tcount[2] is left alone: the far-plane collision running beside this still reads it
+    cudaMemsetAsync(P.tcount, 0, 2 * sizeof(int), st);
+    cudaMemsetAsync(P.tcount + 3, 0, 5 * sizeof(int), st);
+    ++c->tile_stamp;
+    k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, c->tile_stamp, tz_lo, tz_hi, 1);
+    k_tile_mark<<<1, 1, 0, st>>>(P);
+    c->launches += 2;
+    launch_chain_kernels(c, st, true, true);
+}
+
+// ... late half, after the far planes: the rest of the tile update; when it finds active tiles the early half did not
+// know of, the whole chain runs again on the complete lists (exactly what a non-speculative step does); then K7 + packing.
+void launch_chain_late(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi) {
+    Dev &P = c->d;
+    const int nb = (P.ntiles + 127) / 128;
+    k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, c->tile_stamp, tz_lo, tz_hi, 0);
+    k_tile_mode<<<1, 1, 0, st>>>(P, 1);
+    c->launches += 2;
+    P.wq_stamp = c->tile_stamp;
+    P.wq_all = 0;
+    P.tile_cur ^= 1;
+    c->solid_phi_stale = true;
+    launch_chain_kernels(c, st, true, false);
+    launch_gradient_pack(c, st);
+}
+
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
     Dev &P = c->d;
     if (!P.multiphase) return;
     if (P.use_tiles) {
         const int nb = (P.ntiles + 127) / 128;
         if (stepping) {
-            cudaMemsetAsync(P.tcount, 0, 4 * sizeof(int), st);
-            k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp);
-            k_tile_mode<<<1, 1, 0, st>>>(P);
+            cudaMemsetAsync(P.tcount, 0, 8 * sizeof(int), st);
+            k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp, 0, P.ntz - 1, 1);
+            k_tile_mode<<<1, 1, 0, st>>>(P, 0);
+            c->launches += 2;
             P.wq_stamp = c->tile_stamp;
             P.wq_all = 0;
             P.tile_cur ^= 1;
@@ -493,31 +635,10 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
         } else {
             launch_tiles_reset(c, st);
             k_tile_all<<<nb, 128, 0, st>>>(P);  // tcount[2] = 1: the flat kernels run
+            c->launches++;
             c->solid_phi_stale = false;
         }
-        const int grid = P.ntiles < 148 * 32 ? P.ntiles : 148 * 32;
-        const int fgrid = 148 * 8;
-        // K4 (tile-driven) also stamps the warps of the active tiles (stepping only; nG > 0 whenever there is a fluid node)
-        if (P.num_solid > 0) {
-            if (stepping) k_chain_tiles<3><<<grid, 64, 0, st>>>(P, 0);
-            k_chain_flat<3><<<fgrid, 256, 0, st>>>(P);
-        }
-        if (P.nG > 0) {
-            if (stepping) {
-                if (P.k4_smem) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
-                else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, c->tile_stamp);
-            }
-            k_chain_flat<4><<<fgrid, 256, 0, st>>>(P);
-        }
-        if (P.num_fluid > 0) {
-            if (stepping) k_chain_tiles<5><<<grid, 64, 0, st>>>(P, 0);
-            k_chain_flat<5><<<fgrid, 256, 0, st>>>(P);
-        }
-        if (P.num_solid > 0) {
-            if (stepping) k_chain_tiles<6><<<grid, 64, 0, st>>>(P, 0);
-            k_chain_flat<6><<<fgrid, 256, 0, st>>>(P);
-        }
-        c->launches += (stepping ? 2 : 1) * (1 + (P.num_solid > 0 ? 2 : 0) + (P.nG > 0 ? 1 : 0) + (P.num_fluid > 0 ? 1 : 0));
+        launch_chain_kernels(c, st, stepping, false);
         launch_gradient_pack(c, st);
         return;
     }

@@ -158,6 +158,13 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->halo_buf[0] = ctx->halo_buf[1] = ctx->halo_buf[2] = ctx->halo_buf[3] = nullptr;
     ctx->ckpt_mode = 0;
     ctx->ev_ckpt = nullptr;
+    ctx->s_chain = nullptr;
+    ctx->ev_near = ctx->ev_chain = ctx->ev_sum[0] = ctx->ev_sum[1] = nullptr;
+    ctx->sum_host = nullptr;
+    ctx->sum_step[0] = ctx->sum_step[1] = -1;
+    ctx->step_count = 0;
+    ctx->spec_steps = 0;
+    ctx->spec_enabled = getenv("MFLBM_NO_SPEC") ? 0 : 1;
     for (int q = 0; q < 19; q++) ctx->ckpt_f[q] = ctx->ckpt_g[q] = nullptr;
     ctx->ckpt_phi = ctx->ckpt_fc = ctx->ckpt_gc = ctx->ckpt_pc = nullptr;
     ctx->stage = nullptr;
@@ -199,6 +206,13 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         CU(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_out_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_ckpt, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithPriority(&ctx->s_chain, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&ctx->ev_near, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_sum[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_sum[1], cudaEventDisableTiming));
+        CU(cudaMallocHost((void **)&ctx->sum_host, 16 * sizeof(int)));
+        memset(ctx->sum_host, 0, 16 * sizeof(int));
         ctx->ev_phi_valid = false;
         Dev &d = ctx->d;
         d.g.nx = cfg->nx; d.g.ny = cfg->ny; d.g.nz = cfg->nz;
@@ -300,7 +314,10 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
             if (ctx->ckpt_g[q]) cudaFree(ctx->ckpt_g[q]);
         }
     }
-    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi, ctx->ev_out, ctx->ev_out_done, ctx->ev_ckpt};
+    if (ctx->s_chain) cudaStreamDestroy(ctx->s_chain);
+    if (ctx->sum_host) cudaFreeHost(ctx->sum_host);
+    cudaEvent_t evs[] = {ctx->ev_t0, ctx->ev_t1, ctx->ev_slab, ctx->ev_halo, ctx->ev_fork, ctx->ev_phi, ctx->ev_out, ctx->ev_out_done, ctx->ev_ckpt,
+                         ctx->ev_near, ctx->ev_chain, ctx->ev_sum[0], ctx->ev_sum[1]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     delete ctx;
@@ -639,9 +656,10 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
             dev_alloc(ctx, &d.tU[0], nt) || dev_alloc(ctx, &d.tU[1], nt) || dev_alloc(ctx, &d.tquiet, nt) ||
             dev_alloc(ctx, &d.tg_start, nt) || dev_alloc(ctx, &d.ts_start, nt) || dev_alloc(ctx, &d.tf_start, nt) ||
             dev_alloc(ctx, &d.tact, nt) || dev_alloc(ctx, &d.tk3, nt) || dev_alloc(ctx, &d.tk3stamp, nt) ||
-            dev_alloc(ctx, &d.tcount, 4))
+            dev_alloc(ctx, &d.tcount, 12))
             return MFLBM_ERR_CUDA;
     }
+    if (!d.tcount && dev_alloc(ctx, &d.tcount, 12)) return MFLBM_ERR_CUDA;  // [7] is also the sink of Stencil19::load
     size_t n = g.ntot;
     if (d.sparse) {
         if (build_active_set(ctx, walls)) return MFLBM_ERR_CUDA;
@@ -977,6 +995,59 @@ static int collide_timed(mflbm_ctx *ctx, cudaStream_t s, bool odd, int k0, int k
     return 0;
 }
 
+// Speculative early gradient chain (sparse multiphase layout with quiet tiles).  The chain of step t (K3..K6 on the
+// active tiles) is latency-bound and small, the collision is bandwidth-bound and large, and the chain only needs phi(t)
+// around the active tiles.  So: collide the planes around the active tiles FIRST, then run the chain on its own
+// high-priority stream BESIDE the collision of the remaining (far) planes.  Where the active tiles are is a guess -- the
+// layer range of a recent step, read back asynchronously, widened by one layer.  The guess cannot break anything: the
+// early chain reads only what the near-plane collision has already written (layers tz_lo-2..tz_hi+2), and after the far
+// planes the tile update of the rest of the lattice decides on the device whether active tiles were missed, in which case
+// the whole chain runs again on the complete lists, exactly like a plain step (kernels_gradient.cu, launch_chain_late).
+struct SpecPlan {
+    bool on;
+    int tz_lo, tz_hi;  // tile layers of the early chain
+    int k_lo, k_hi;    // planes collided first on their behalf (layers tz_lo-2..tz_hi+2)
+};
+
+static SpecPlan spec_plan(mflbm_ctx *ctx) {
+    SpecPlan p{false, 0, 0, 0, 0};
+    const Dev &d = ctx->d;
+    const mflbm_config &cfg = ctx->cfg;
+    if (!ctx->spec_enabled || !d.multiphase || !d.sparse || !d.use_tiles || d.wq_all) return p;
+    int force_lo = -1, force_hi = -1;
+    if (const char *f = getenv("MFLBM_SPEC_FORCE"))  // test knob "lo:hi": pretend the active tiles are in these layers
+        sscanf(f, "%d:%d", &force_lo, &force_hi);
+    // most recent summary that has arrived (requested after the chain of an earlier step)
+    int best = -1;
+    for (int sl = 0; sl < 2; sl++)
+        if (ctx->sum_step[sl] >= 0 && ctx->sum_step[sl] + 4 >= ctx->step_count && cudaEventQuery(ctx->ev_sum[sl]) == cudaSuccess &&
+            (best < 0 || ctx->sum_step[sl] > ctx->sum_step[best]))
+            best = sl;
+    const int nz = d.g.nz;
+    if (force_lo >= 0 && force_hi >= force_lo) {
+        p.tz_lo = std::min(force_lo, d.ntz - 1);
+        p.tz_hi = std::min(force_hi, d.ntz - 1);
+    } else {
+        if (best < 0) return p;
+        const int *t = ctx->sum_host + 8 * best;
+        if (t[2] != 0 || t[0] <= 0 || t[5] <= 0 || t[6] <= 0) return p;  // flat sweep last time / no active tile at all
+        if ((long long)t[0] * 8 > (long long)d.ntiles) return p;
+        p.tz_lo = std::max(0, (d.ntz - t[5]) - 1);
+        p.tz_hi = std::min(d.ntz - 1, (t[6] - 1) + 1);
+    }
+    // layer L holds the planes k = 4L-3 .. 4L
+    p.k_lo = std::max(1, 4 * (p.tz_lo - 2) - 3);
+    p.k_hi = std::min(nz, 4 * (p.tz_hi + 2));
+    if (p.k_hi < p.k_lo || 2 * (p.k_hi - p.k_lo + 1) > nz) return p;  // not worth it
+    // ghost planes that only exist after the halo exchange / the periodic wrap of this step must stay out of reach
+    const bool ghost_lo = (ctx->comm && (cfg.kper == 1 || cfg.idz != 0)) || (!ctx->comm && cfg.kper == 1);
+    const bool ghost_hi = (ctx->comm && (cfg.kper == 1 || cfg.idz != cfg.npz - 1)) || (!ctx->comm && cfg.kper == 1);
+    if (ghost_lo && p.tz_lo - 2 <= 0) return p;
+    if (ghost_hi && p.tz_hi + 2 >= ((nz + 4) >> 2)) return p;
+    p.on = true;
+    return p;
+}
+
 // main_iteration_kernel for one ntime
 static int step_impl(mflbm_ctx *ctx, int ntime) {
     const mflbm_config &cfg = ctx->cfg;
@@ -986,25 +1057,73 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
     const bool odd = (ntime % 2) != 0;
     cudaStream_t s = ctx->s_main;
     if (tiles_prepare(ctx, s)) return fail(ctx, MFLBM_ERR_CUDA, "quiet-tile setup failed");
-    if (ctx->comm) {
-        // boundary slabs first, exchange on the high-priority halo stream while the interior runs
-        // (MP/Main_multiphase.F90:358-387, :423-458)
-        const int iz = cfg.iz_async > 0 ? cfg.iz_async : 1;
-        if (collide_timed(ctx, s, odd, 1, iz) || collide_timed(ctx, s, odd, nz - iz + 1, nz)) return MFLBM_ERR_CUDA;
-        CU(cudaEventRecord(ctx->ev_slab, s));
-        CU(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_slab, 0));
-        if (halo_exchange(ctx, ctx->s_halo, odd)) return MFLBM_ERR_NCCL;
-        CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
-        if (collide_timed(ctx, s, odd, iz + 1, nz - iz)) return MFLBM_ERR_CUDA;
-        CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
+    const SpecPlan sp = spec_plan(ctx);
+    ctx->step_count++;
+    const int iz = cfg.iz_async > 0 ? cfg.iz_async : 1;
+    if (sp.on) {
+        // planes collided first: around the active tiles, the planes the inlet / outlet kernels work on, and (with
+        // neighbours) the boundary slabs the halo exchange waits for
+        std::vector<char> first((size_t)nz + 2, 0);
+        for (int k = sp.k_lo; k <= sp.k_hi; k++) first[k] = 1;
+        if (ctx->open_z && cfg.idz == 0) first[1] = first[std::min(2, nz)] = 1;
+        if (ctx->open_z && cfg.idz == cfg.npz - 1) first[nz] = first[std::max(1, nz - 1)] = 1;
+        if (ctx->comm)
+            for (int k = 1; k <= iz; k++) first[k] = first[nz + 1 - k] = 1;
+        auto collide_runs = [&](char want) -> int {
+            for (int k = 1; k <= nz;) {
+                if (first[k] != want) { k++; continue; }
+                int e = k;
+                while (e + 1 <= nz && first[e + 1] == want) e++;
+                if (collide_timed(ctx, s, odd, k, e)) return MFLBM_ERR_CUDA;
+                k = e + 1;
+            }
+            return 0;
+        };
+        if (collide_runs(1)) return MFLBM_ERR_CUDA;
+        if (ctx->comm) {
+            CU(cudaEventRecord(ctx->ev_slab, s));
+            CU(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_slab, 0));
+            if (halo_exchange(ctx, ctx->s_halo, odd)) return MFLBM_ERR_NCCL;
+            CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
+        }
+        launch_bc(ctx, s, odd);  // inlet / outlet planes are done; they never meet the halo faces (open domain: end ranks only)
+        CU(cudaEventRecord(ctx->ev_near, s));
+        CU(cudaStreamWaitEvent(ctx->s_chain, ctx->ev_near, 0));
+        launch_chain_early(ctx, ctx->s_chain, sp.tz_lo, sp.tz_hi);
+        CU(cudaEventRecord(ctx->ev_chain, ctx->s_chain));
+        if (collide_runs(0)) return MFLBM_ERR_CUDA;  // the far planes, beside the early chain
+        CU(cudaEventRecord(ctx->ev_phi, s));
+        ctx->ev_phi_valid = true;
+        if (ctx->comm) CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
+        CU(cudaStreamWaitEvent(s, ctx->ev_chain, 0));
+        launch_chain_late(ctx, s, sp.tz_lo, sp.tz_hi);
+        ctx->spec_steps++;
     } else {
-        if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
-        if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
+        if (ctx->comm) {
+            // boundary slabs first, exchange on the high-priority halo stream while the interior runs
+            // (MP/Main_multiphase.F90:358-387, :423-458)
+            if (collide_timed(ctx, s, odd, 1, iz) || collide_timed(ctx, s, odd, nz - iz + 1, nz)) return MFLBM_ERR_CUDA;
+            CU(cudaEventRecord(ctx->ev_slab, s));
+            CU(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_slab, 0));
+            if (halo_exchange(ctx, ctx->s_halo, odd)) return MFLBM_ERR_NCCL;
+            CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
+            if (collide_timed(ctx, s, odd, iz + 1, nz - iz)) return MFLBM_ERR_CUDA;
+            CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
+        } else {
+            if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
+            if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
+        }
+        CU(cudaEventRecord(ctx->ev_phi, s));  // nothing below writes phi at a fluid node (BC: ghost planes, K3: solid nodes)
+        ctx->ev_phi_valid = true;
+        launch_bc(ctx, s, odd);
+        launch_color_gradient(ctx, s, true);
     }
-    CU(cudaEventRecord(ctx->ev_phi, s));  // nothing below writes phi at a fluid node (BC: ghost planes, K3: solid nodes)
-    ctx->ev_phi_valid = true;
-    launch_bc(ctx, s, odd);
-    launch_color_gradient(ctx, s, true);
+    if (ctx->d.use_tiles && ctx->spec_enabled) {  // where the active tiles were: feeds the plan of a later step
+        const int sl = (int)(ctx->step_count & 1);
+        CU(cudaMemcpyAsync(ctx->sum_host + 8 * sl, ctx->d.tcount, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(ctx->ev_sum[sl], s));
+        ctx->sum_step[sl] = ctx->step_count;
+    }
     return check_launch(ctx);
 }
 
@@ -1129,10 +1248,10 @@ extern "C" int mflbm_checkpoint_begin(mflbm_ctx *ctx) {
     Dev &d = ctx->d;
     cudaStream_t s = ctx->s_main;
     if (d.multiphase && ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, s);  // the reference's phi on every listed solid node
-    const size_t plane = (size_t)d.g.sxy + 32;
+    const size_t plane = (size_t)d.g.sxy + 32, plane19 = (size_t)19 * d.g.sxy + 32;  // sizes of the plane fields as allocated
     size_t need = 0;
     for (int q = 0; q < 19; q++) need += pdf_elems(d, q) * (d.multiphase ? 2 : 1);
-    need += (d.multiphase ? (size_t)d.g.ntot + 20 * plane : 0) + 19 * plane;
+    need += (d.multiphase ? (size_t)d.g.ntot + plane19 + plane : 0) + plane19;
     need *= sizeof(double);
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
@@ -1148,9 +1267,9 @@ extern "C" int mflbm_checkpoint_begin(mflbm_ctx *ctx) {
             ok = snap(&ctx->ckpt_f[q], d.f[q], pdf_elems(d, q));
             if (ok && d.multiphase) ok = snap(&ctx->ckpt_g[q], d.gg[q], pdf_elems(d, q));
         }
-        if (ok) ok = snap(&ctx->ckpt_fc, d.f_convec, 19 * plane);
+        if (ok) ok = snap(&ctx->ckpt_fc, d.f_convec, plane19);
         if (ok && d.multiphase)
-            ok = snap(&ctx->ckpt_phi, d.phi, (size_t)d.g.ntot) && snap(&ctx->ckpt_gc, d.g_convec, 19 * plane) && snap(&ctx->ckpt_pc, d.phi_convec, plane);
+            ok = snap(&ctx->ckpt_phi, d.phi, (size_t)d.g.ntot) && snap(&ctx->ckpt_gc, d.g_convec, plane19) && snap(&ctx->ckpt_pc, d.phi_convec, plane);
         if (!ok) {  // allocation failed after all: fall back to the frozen-context mode
             cudaGetLastError();
             ckpt_release(ctx, s);
@@ -1402,6 +1521,8 @@ extern "C" int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nq
 }
 
 extern "C" long long mflbm_launch_count(const mflbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+// internal (tests, bench.py): how many steps of this context ran with the speculative early gradient chain
+extern "C" long long mflbmx_spec_steps(const mflbm_ctx *ctx) { return ctx ? ctx->spec_steps : 0; }
 extern "C" long long mflbm_device_bytes(const mflbm_ctx *ctx) { return ctx ? ctx->bytes : 0; }
 
 // Internal (not part of include/mflbm.h): host-only self-test of the node numbering + compressed adjacency, callable

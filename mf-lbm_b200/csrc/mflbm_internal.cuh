@@ -155,8 +155,10 @@ struct Dev {
     unsigned char *tquiet;   // 1: tile is quiet
     int *tg_start, *ts_start, *tf_start;  // [ntiles+1] CSR ranges of gcell / the solid list / the fluid list (sorted by tile)
     int *tact, *tk3;         // [ntiles] active tiles (K4,K5,K6) / tiles within one tile of an active tile (K3), per step
-    int *tcount;             // [4] lengths of tact, tk3; [2] = 1: most tiles are active, the chain of this step ran over the
-                             // whole lists (flat, grid-stride) and every warp counts as active; [3] unused
+    int *tcount;             // [8]: [0], [1] lengths of tact, tk3; [2] = 1: most tiles are active, the chain of this step ran
+                             // over the whole lists (flat sweep) and every warp counts as active; [3] = 1: tile-driven
+                             // pass selected; [4] active tiles found by the early half of a speculative step; [5], [6]
+                             // layer range of the active tiles (ntz - min tz, max tz + 1; 0 = none); [7] scratch sink
     int *tk3stamp;           // [ntiles] step stamp guarding the tk3 append
     // per warp of 32 consecutive A nodes: stamp of the last tile update that found one of its nodes in an ACTIVE tile.
     // The collision kernel reads this one warp-uniform word (address known from n alone) instead of chaining
@@ -248,6 +250,15 @@ struct mflbm_ctx {
     size_t out_elems[5];
     int out_pending;                   // field mask of the staged output in flight (0: none)
     // checkpoint staging (mflbm_checkpoint_begin / _fetch / _end)
+    // speculative early gradient chain (step_impl): layer range of the active tiles as of a recent step, read back
+    // asynchronously (heuristic only -- a wrong guess costs time, never correctness)
+    cudaStream_t s_chain;
+    cudaEvent_t ev_near, ev_chain, ev_sum[2];
+    int *sum_host;                     // pinned, 2 x 8 ints (copies of Dev::tcount)
+    long long sum_step[2];             // step counter at which each slot was requested (-1: never)
+    long long step_count;
+    int spec_enabled;                  // MFLBM_NO_SPEC=1 switches it off
+    long long spec_steps;              // steps that ran speculatively (mflbm_tile_stats-style diagnostics)
     int ckpt_mode;                     // 0 none, 1 staged (device snapshot in ckpt_*), 2 direct (context frozen)
     double *ckpt_f[19], *ckpt_g[19], *ckpt_phi, *ckpt_fc, *ckpt_gc, *ckpt_pc;
     cudaEvent_t ev_ckpt;
@@ -295,6 +306,8 @@ void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);
 int tiles_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_curvature(mflbm_ctx *c, cudaStream_t st);
 void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st);
+void launch_chain_early(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
+void launch_chain_late(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
 void launch_macro(mflbm_ctx *c, cudaStream_t st);

@@ -49,7 +49,8 @@ int mfd_set_walls_window(void *h, const int8_t *w, int nplanes, int wk0) {
         // (smoothing 4 + ISO8 2 + list ghosts 3, + the 2 ghost planes set_walls fills); a smaller one would be read out of bounds
         const int nzG = d->c.nzGlobal, nz = nzG / (d->c.npz > 0 ? d->c.npz : 1);
         const int ks0 = d->idz * nz + 1, ks1 = d->idz * nz + nz, wk1 = wk0 + nplanes - 1;
-        const bool lo_ok = wk0 <= ks0 - 10 || (d->c.kper == 0 && wk0 <= 1), hi_ok = wk1 >= ks1 + 10 || (d->c.kper == 0 && wk1 >= nzG);
+        const bool whole = wk0 <= 1 && wk1 >= nzG;  // the whole lattice: set_walls wraps it itself when z is periodic
+        const bool lo_ok = whole || wk0 <= ks0 - 10 || (d->c.kper == 0 && wk0 <= 1), hi_ok = whole || wk1 >= ks1 + 10 || (d->c.kper == 0 && wk1 >= nzG);
         if (!lo_ok || !hi_ok) {
             d->error = "wall window too small: it must reach the lattice end or extend >= 10 planes beyond the slab";
             return -1;

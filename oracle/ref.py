@@ -21,29 +21,30 @@ class _Desc(C.Structure):
                 ("elem", C.c_int)]
 
 
-def lib_path(solver):
-    return os.path.join(REF_DIR, "libmflbm_ref_%s.so" % solver)
+def lib_path(solver, fast=False):
+    return os.path.join(REF_DIR, "libmflbm_ref_%s%s.so" % (solver, "_fast" if fast else ""))
 
 
-def build(solver="mp"):
+def build(solver="mp", fast=False):
     """translate + compile (needs /root/reference); returns the .so path or None"""
     if not os.path.isdir(REFERENCE_ROOT):
-        return lib_path(solver) if os.path.exists(lib_path(solver)) else None
+        return lib_path(solver, fast) if os.path.exists(lib_path(solver, fast)) else None
     subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
-    return lib_path(solver)
+    return lib_path(solver, fast)
 
 
-def available(solver="mp"):
-    return os.path.exists(lib_path(solver)) or os.path.isdir(REFERENCE_ROOT)
+def available(solver="mp", fast=False):
+    return os.path.exists(lib_path(solver, fast)) or os.path.isdir(REFERENCE_ROOT)
 
 
 _LIBS = {}
 
 
-def _load(solver):
-    if solver in _LIBS:
-        return _LIBS[solver]
-    path = build(solver)
+def _load(solver, fast=False):
+    key = (solver, fast)
+    if key in _LIBS:
+        return _LIBS[key]
+    path = build(solver, fast)
     if path is None or not os.path.exists(path):
         raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
     lib = C.CDLL(path)
@@ -58,7 +59,7 @@ def _load(solver):
     lib.ref_call.argtypes = [C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     lib.ref_sub_name.argtypes = [C.c_int]
     lib.ref_sub_name.restype = C.c_char_p
-    _LIBS[solver] = lib
+    _LIBS[key] = lib
     return lib
 
 
@@ -66,8 +67,8 @@ class Ref:
     """The module state of ONE reference solver ("mp" = multiphase_3D, "sp" = singlephase_3D) in this process.
     Module variables are process globals, exactly like in the Fortran program: one instance at a time."""
 
-    def __init__(self, solver="mp"):
-        self.lib = _load(solver)
+    def __init__(self, solver="mp", fast=False):
+        self.lib = _load(solver, fast)
         self.solver = solver
 
     def subroutines(self):

@@ -6,11 +6,11 @@ from oracle.oracle import FLUID_DTYPE, SOLID_DTYPE
 from oracle.ref import Ref
 
 
-def ref_from_oracle(o):
+def ref_from_oracle(o, fast=False):
     """Module variables and arrays of the reference program <- the oracle's state (after its setup): what the reference's
     own initialisation would leave behind for main_iteration_kernel."""
     p = o.p
-    r = Ref("mp" if o.mp else "sp")
+    r = Ref("mp" if o.mp else "sp", fast=fast)
     r.set(nx=o.nx, ny=o.ny, nz=o.nz, nxglobal=p.nxG, nyglobal=p.nyG, nzglobal=p.nzG, idx=0, idy=0, idz=p.idz, npx=1, npy=1,
           npz=p.npz, id=0, iper=0, jper=p.jper, kper=p.kper, domain_wall_status_x_min=p.wsx0, domain_wall_status_x_max=p.wsx1,
           domain_wall_status_y_min=p.wsy0, domain_wall_status_y_max=p.wsy1, domain_wall_status_z_min=p.wsz0,

@@ -156,3 +156,31 @@ def test_quiet_tiles_long_run_bit_exact(ca):
         compare_state(ctx, o, 0.0, sparse=True)
     assert seen_quiet > 0, "the run never had a quiet tile: the skipping path was not exercised"
     ctx.close()
+
+
+@pytest.mark.parametrize("force", [None, "30:31", "0:3"], ids=["guessed", "missed", "partly"])
+def test_speculative_early_chain_is_exact(force, monkeypatch):
+    """Speculative step schedule (DESIGN.md "Step schedule"): the gradient chain of the active tiles runs beside the
+    collision of the far planes.  A long duct so that the planner switches it on; strict build, bit-exact against the oracle
+    whether the guessed layer range is right, completely wrong (every active tile is "missed" and the chain re-runs on the
+    full lists) or partly right."""
+    if force:
+        monkeypatch.setenv("MFLBM_SPEC_FORCE", force)
+    rng = np.random.default_rng(23)
+    nz = 160
+    wg = (rng.random((24, 22, nz)) < 0.22).astype(np.int8)
+    wg[:, :, :6] = 0
+    wg[:, :, -6:] = 0
+    o = make_oracle(nxG=24, nyG=22, nzG=nz, walls_global=wg, la_nu2=0.04, interface_z0=7.0, ca_0=2e-3, n_exclude_inlet=0,
+                    n_exclude_outlet=0)
+    ctx = ctx_from_oracle(o, strict=True, kernel_variant=2)
+    o.color_gradient(); ctx.color_gradient()
+    t = 1
+    for nsteps in (3, 40, 61):
+        _run_both(o, ctx, nsteps, t)
+        t += nsteps
+        compare_state(ctx, o, 0.0, sparse=True)
+    assert ctx.spec_steps > 50, ctx.spec_steps
+    nt, nq = ctx.tile_stats()
+    assert nq > 0
+    ctx.close()

@@ -40,19 +40,19 @@ def _bentheimer_crop(n=96):
     return np.ascontiguousarray(w[i0:i0 + n, i0:i0 + n, k0:k0 + n])
 
 
-def _check(o, strict, layout, steps_strict=10):
+def _check(o, strict, layout, steps_strict=10, tol_fma=1e-12):
     ctx = ctx_from_oracle(o, strict=strict, kernel_variant=layout)
     sp = layout == 2
     if o.mp:
         o.color_gradient()
         ctx.color_gradient()
-        compare_state(ctx, o, 0.0 if strict else 1e-12, sparse=sp)
+        compare_state(ctx, o, 0.0 if strict else tol_fma, sparse=sp)
     if strict:
         _run(o, ctx, steps_strict)
         compare_state(ctx, o, 0.0, sparse=sp)
     else:
         _run(o, ctx, 2)  # one odd + one even step
-        compare_state(ctx, o, 1e-12, sparse=sp)
+        compare_state(ctx, o, tol_fma, sparse=sp)
     ctx.close()
 
 
@@ -73,7 +73,9 @@ def test_bentheimer_crop_imbibition_case4(strict, layout):
     w[:, :, -8:] = 0
     o = make_oracle(nxG=96, nyG=96, nzG=96, walls_global=w, la_nu2=0.04, theta_deg=150.0, ca_0=100e-6, sa_inject=0.0,
                     initial_fluid_distribution_option=2, n_exclude_inlet=8, n_exclude_outlet=8)
-    _check(o, strict, layout)
+    # FMA build: the normalised gradient n = grad(phi) / |grad(phi)| and the wetting alteration (1 / sqrt(1 - t^2), theta = 150)
+    # amplify last-bit differences where |grad(phi)| is just above the 1e-6 cut-off; measured 8e-9 on n, 2e-10 on the populations
+    _check(o, strict, layout, tol_fma=1e-7)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -89,7 +91,7 @@ def test_bentheimer_crop_fractional_flow_case5(strict, layout):
     rng = np.random.default_rng(20261018)
     o.field("phi")[...] = np.where(rng.random(o.field("phi").shape) > 0.4, -1.0, 1.0)
     o.init_pdf()
-    _check(o, strict, layout, steps_strict=8)
+    _check(o, strict, layout, steps_strict=8, tol_fma=1e-7)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -107,6 +109,7 @@ def test_monitor_steady_phasefield(layout):
     phi_old <- phi; phi_old starts as a copy of phi (MP/Init_multiphase.F90:341-347)."""
     o = make_oracle(modify_geometry_cmd=1, steady_state_option=2, ca_0=5e-3)
     ctx = ctx_from_oracle(o, kernel_variant=layout)
+    ctx.upload(phi_old=o.field("phi_old"))  # what the driver uploads when steady_state_option == 2 (fortran/mflbm_iso_c.f90)
     o.color_gradient(); ctx.color_gradient()
     t = 1
     for n in (20, 30):

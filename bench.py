@@ -448,7 +448,7 @@ def main():
                        "population_layout": "auto (kernel_variant=%d)" % args.variant, "setup_s": round(setup_s, 1),
                        "device_bytes_per_gpu": drv.device_bytes,
                        "quiet_tile_fraction": main_r["quiet"], "state": args.state,
-                       "speculative_chain_steps": int(main_r["spec"]),
+                       "speculative_chain_steps": int(main_r["spec"]), "tile_summary": drv.spec_info(),
                        "fluid_nodes_per_rank": [int(v) for v in per_rank_pore],
                        "ms_per_step_per_rank": [round(v, 4) for v in per_rank_ms]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -116,6 +116,8 @@ def load(strict=False):
     lib.mflbm_device_bytes.restype = C.c_longlong
     lib.mflbmx_spec_steps.argtypes = [vp]
     lib.mflbmx_spec_steps.restype = C.c_longlong
+    lib.mflbmx_spec_info.argtypes = [vp, C.POINTER(C.c_int * 16)]
+    lib.mflbmx_spec_info.restype = None
     lib.mflbm_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte * 128)]
     lib.mflbm_geometry_preprocess.argtypes = [C.POINTER(GeometryConfig), C.c_void_p, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

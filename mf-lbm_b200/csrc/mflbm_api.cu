@@ -163,8 +163,12 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->sum_host = nullptr;
     ctx->sum_step[0] = ctx->sum_step[1] = -1;
     ctx->step_count = 0;
+    ctx->sum_next = 0;
     ctx->spec_steps = 0;
-    ctx->spec_enabled = getenv("MFLBM_NO_SPEC") ? 0 : 1;
+    // MEASURED (r02_m8 / m11, B200): exact, but no gain -- C3 5.98 ms/step with it against 5.91 without, the 1536x1536x192
+    // slab 25.1 against 24.4 (under sw_power_cap): the collision kernel holds every register of an SM, the chain kernels
+    // only trickle in as its blocks retire and slow it down by what they gain.  Off unless MFLBM_SPEC=1.
+    ctx->spec_enabled = (getenv("MFLBM_SPEC") && atoi(getenv("MFLBM_SPEC"))) ? 1 : 0;
     for (int q = 0; q < 19; q++) ctx->ckpt_f[q] = ctx->ckpt_g[q] = nullptr;
     ctx->ckpt_phi = ctx->ckpt_fc = ctx->ckpt_gc = ctx->ckpt_pc = nullptr;
     ctx->stage = nullptr;
@@ -387,7 +391,12 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
             for (int i = 0; i <= nx + 1; i++) {
                 if (isA(i, j, k)) continue;
                 if (k > 2 && k < nz - 1) continue;  // outside the cell-addressable zone: served by compact link slots
-                bool s = false;
+                // Ghost-plane cells that are fluid by their own wall flag (= the flag of the periodic image / of the
+                // neighbour slab's boundary plane) always get storage: the reference's exchange copies their slots into the
+                // boundary plane unconditionally (MP/Mpi.F90:374-396, :497-519), and right after an upload they may hold
+                // values nothing else reproduces (initial_fluid_distribution_option 6 draws phi in the ghost layers
+                // independently of their images, MP/Init_multiphase.F90:276-311).
+                bool s = (k == 0 || k == nz + 1) && i >= 1 && i <= nx && j >= 1 && j <= ny && W(i, j, k) == 0;
                 for (int q = 1; q < 19 && !s; q++) s = isA(i + EX(q), j + EY(q), k + EZ(q));
                 if (s) {
                     idx[B(i, j, k)] = -2;
@@ -1019,9 +1028,9 @@ static SpecPlan spec_plan(mflbm_ctx *ctx) {
         sscanf(f, "%d:%d", &force_lo, &force_hi);
     // most recent summary that has arrived (requested after the chain of an earlier step)
     int best = -1;
+    // (mflbm_run queues steps far ahead of the device, so "recent" can be tens of steps old: the margin grows with the age)
     for (int sl = 0; sl < 2; sl++)
-        if (ctx->sum_step[sl] >= 0 && ctx->sum_step[sl] + 4 >= ctx->step_count && cudaEventQuery(ctx->ev_sum[sl]) == cudaSuccess &&
-            (best < 0 || ctx->sum_step[sl] > ctx->sum_step[best]))
+        if (ctx->sum_step[sl] >= 0 && cudaEventQuery(ctx->ev_sum[sl]) == cudaSuccess && (best < 0 || ctx->sum_step[sl] > ctx->sum_step[best]))
             best = sl;
     const int nz = d.g.nz;
     if (force_lo >= 0 && force_hi >= force_lo) {
@@ -1031,9 +1040,9 @@ static SpecPlan spec_plan(mflbm_ctx *ctx) {
         if (best < 0) return p;
         const int *t = ctx->sum_host + 8 * best;
         if (t[2] != 0 || t[0] <= 0 || t[5] <= 0 || t[6] <= 0) return p;  // flat sweep last time / no active tile at all
-        if ((long long)t[0] * 8 > (long long)d.ntiles) return p;
-        p.tz_lo = std::max(0, (d.ntz - t[5]) - 1);
-        p.tz_hi = std::min(d.ntz - 1, (t[6] - 1) + 1);
+        const int margin = 1 + (int)std::min<long long>(6, (ctx->step_count - ctx->sum_step[best]) / 32);
+        p.tz_lo = std::max(0, (d.ntz - t[5]) - margin);
+        p.tz_hi = std::min(d.ntz - 1, (t[6] - 1) + margin);
     }
     // layer L holds the planes k = 4L-3 .. 4L
     p.k_lo = std::max(1, 4 * (p.tz_lo - 2) - 3);
@@ -1118,8 +1127,12 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
         launch_bc(ctx, s, odd);
         launch_color_gradient(ctx, s, true);
     }
-    if (ctx->d.use_tiles && ctx->spec_enabled) {  // where the active tiles were: feeds the plan of a later step
-        const int sl = (int)(ctx->step_count & 1);
+    // Where the active tiles were: feeds the plan of later steps.  mflbm_run queues steps far ahead of the device, so a
+    // request is only made every 32nd step (and early on), alternating between two slots: by the time a slot is requested
+    // again (64 steps later) its previous copy has long arrived, and one of the two is always readable.
+    if (ctx->d.use_tiles && ctx->spec_enabled && (ctx->step_count % 32 == 0 || ctx->step_count == 2 || ctx->step_count == 8)) {
+        const int sl = ctx->sum_next;
+        ctx->sum_next ^= 1;
         CU(cudaMemcpyAsync(ctx->sum_host + 8 * sl, ctx->d.tcount, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaEventRecord(ctx->ev_sum[sl], s));
         ctx->sum_step[sl] = ctx->step_count;
@@ -1523,6 +1536,10 @@ extern "C" int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nq
 extern "C" long long mflbm_launch_count(const mflbm_ctx *ctx) { return ctx ? ctx->launches : 0; }
 // internal (tests, bench.py): how many steps of this context ran with the speculative early gradient chain
 extern "C" long long mflbmx_spec_steps(const mflbm_ctx *ctx) { return ctx ? ctx->spec_steps : 0; }
+// internal: the two summary slots (copies of Dev::tcount[0..7]) as last read back, for diagnostics
+extern "C" void mflbmx_spec_info(const mflbm_ctx *ctx, int out[16]) {
+    for (int n = 0; n < 16; n++) out[n] = (ctx && ctx->sum_host) ? ctx->sum_host[n] : 0;
+}
 extern "C" long long mflbm_device_bytes(const mflbm_ctx *ctx) { return ctx ? ctx->bytes : 0; }
 
 // Internal (not part of include/mflbm.h): host-only self-test of the node numbering + compressed adjacency, callable

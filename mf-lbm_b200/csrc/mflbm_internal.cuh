@@ -257,6 +257,7 @@ struct mflbm_ctx {
     int *sum_host;                     // pinned, 2 x 8 ints (copies of Dev::tcount)
     long long sum_step[2];             // step counter at which each slot was requested (-1: never)
     long long step_count;
+    int sum_next;                      // slot of the next request
     int spec_enabled;                  // MFLBM_NO_SPEC=1 switches it off
     long long spec_steps;              // steps that ran speculatively (mflbm_tile_stats-style diagnostics)
     int ckpt_mode;                     // 0 none, 1 staged (device snapshot in ckpt_*), 2 direct (context frozen)

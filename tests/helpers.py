@@ -82,16 +82,14 @@ def active_mask(o):
 
 
 def slot_mask(o, q):
-    """Sparse layout: cells whose slot q is live storage = fluid nodes, every neighbour of a fluid node inside the
-    cell-addressable zone (planes 0..2 and nz-1..nz+1, used by the BC / halo kernels), and outside the zone exactly the
-    non-fluid cells y whose slot q a fluid node streams through: y + e_q fluid (the compact link slots).  All other
-    slots are dead storage that neither the reference nor mflbm_download ever touches after initialisation."""
+    """Sparse layout: cells whose slot q is LIVE storage = the fluid nodes (the even step reads all 19 own slots) and every
+    non-fluid cell y of the 0..n+1 box whose slot q a fluid node streams through, i.e. y + e_q is fluid (the only node that
+    reads or writes slot q at y in the odd step is y + e_q; the inlet / outlet kernels and the z exchange feed exactly those
+    slots).  All other slots are dead storage: nothing ever consumes them, the reference's exchange merely copies them
+    around (e.g. into the slots of a solid node behind the periodic seam), and mflbm_download may leave them untouched."""
     a = fluid_mask(o)
     nx, ny, nz = a.shape
-    zone = np.zeros(a.shape, bool)
-    zone[:, :, :3] = True
-    zone[:, :, nz - 3:] = True
-    m = a | (active_mask(o) & zone)
+    m = a.copy()
     if q:
         # y + e_q in A  <=>  shift the fluid mask by -e_q
         ex, ey, ez = EX[q], EY[q], EZ[q]

@@ -56,8 +56,9 @@ typedef struct {
     int32_t nx, ny, nz;             /* local slab (MP/Module.F90:80) */
     int32_t nxGlobal, nyGlobal, nzGlobal;
     int32_t idz, npz;               /* slab position; x,y undivided (MP/IO_multiphase.F90:495-498) */
-    int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference); jper = 1 is not
-                                       supported yet: mflbm_create returns MFLBM_ERR_ARG */
+    int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference).  jper = 1 (y is never
+                                       decomposed: the reference exchanges with itself, MP/Mpi.F90:22-40, :147-207): one z
+                                       slab only (npz = 1, else MFLBM_ERR_ARG), always the sparse population layout */
     int32_t domain_wall_status_z_min, domain_wall_status_z_max;
     int32_t inlet_BC, outlet_BC;    /* 1 velocity / convective, 2 Zou-He pressure */
     int32_t porous_plate_cmd, Z_porous_plate;
@@ -68,7 +69,8 @@ typedef struct {
     int32_t use_nccl;               /* 1: z-halo exchange between ranks with ncclSend/ncclRecv */
     int32_t kernel_variant;         /* population layout: 0 = auto (sparse active-node list when porosity <= 0.8, else dense),
                                        1 = dense (the reference's direct addressing), 2 = sparse.  porous_plate_cmd != 0
-                                       always runs dense (the plate copies from arbitrary nodes).  Results are identical. */
+                                       always runs dense (the plate copies from arbitrary nodes), jper = 1 always sparse
+                                       (the y wrap is part of its adjacency).  Results are identical. */
     int32_t reserved_i[7];
     double la_nui1, la_nui2;        /* 1/nu1, 1/nu2 (MP/Init_multiphase.F90:120-121) */
     double gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;

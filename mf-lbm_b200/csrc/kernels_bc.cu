@@ -18,7 +18,23 @@ namespace mflbm {
 // Every cell touched for a column whose boundary node is fluid is a D3Q19 neighbour of that fluid node,
 // hence active; columns whose boundary node is solid are skipped on the sparse layout (the reference's
 // blend new*(1-w)+old*w leaves them unchanged).
-#define X(c) (P.sparse ? P.smap[(c)] : (c))
+// y-periodic lattice (sparse layout only): a ghost-row cell (j = 0 or ny+1) of an interior plane stands for its periodic
+// image -- the reference's y exchange keeps such rows equal to the image rows for k = 1..nz (MP/Mpi.F90:147-180), here the
+// image row is the only storage.  Ghost-PLANE cells behind the seam are real storage when z is not periodic.
+__device__ __forceinline__ int bc_index(const Dev &P, int c) {
+    if (!P.sparse) return c;
+    if (P.jper) {
+        unsigned ix, jy, kz;
+        P.g.coords3(c, ix, jy, kz);
+        const int j = (int)jy - 3, k = (int)kz - 3;
+        if (k >= 1 && k <= P.g.nz) {
+            if (j == 0) c += P.g.sx * P.g.ny;
+            else if (j == P.g.ny + 1) c -= P.g.sx * P.g.ny;
+        }
+    }
+    return P.smap[c];
+}
+#define X(c) bc_index(P, (c))
 
 __device__ __forceinline__ void phi_inlet_ghost(const Dev &P, int i, int j, int wi) {
     const int c0 = P.g.cell(i, j, 0);

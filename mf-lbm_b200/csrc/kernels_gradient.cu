@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(128) k_tile_static(const Dev P, const unsigned
     if (i > nx + 3) return;
     const int c = P.g.cell(i, j, k);
     const int t = P.g.tile_of(c, P.ntx, P.nty);
+    if (P.jper && (j <= 0 || j >= ny + 1)) {  // y ghost rows are rewritten by the periodic wrap every step: always unknown
+        tile_or(P.tstat, t, TILE_X);
+        return;
+    }
     if (k <= 0 || k >= nz + 1) {
         // ghost planes filled by the periodic wrap / the halo exchange: always X.  Ghost planes rewritten every step by
         // an inlet / outlet kernel (columns 1..nx x 1..ny): that kernel records the class of what it writes

@@ -312,6 +312,32 @@ void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push) {
     c->launches++;
 }
 
+// y-periodic lattice: the four phi ghost rows on each side, MP/Mpi.F90:633-655 (pack) and :729-790 (update): rows
+// k = 1..nz, and with z periodic too the x edges, which are the same copies applied to the z ghost planes k_wrap_z has
+// just filled.  (The populations need no copies: the adjacency wraps, see build_active_host.)
+__global__ void k_wrap_y_phi(const Dev P, int k0, int k1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int k = (int)blockIdx.y + k0;
+    if (i > P.g.nx || k > k1) return;
+    const int ny = P.g.ny;
+#pragma unroll
+    for (int jj = 1; jj <= 4; jj++) {
+        const double lo = P.phi[P.g.cell(i, jj, k)];
+        const double hi = P.phi[P.g.cell(i, ny + jj - 4, k)];
+        P.phi[P.g.cell(i, jj - 4, k)] = hi;
+        P.phi[P.g.cell(i, jj + ny, k)] = lo;
+    }
+}
+
+void launch_wrap_y_phi(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.multiphase) return;
+    const int k0 = P.kper ? -3 : 1, k1 = P.kper ? P.g.nz + 4 : P.g.nz;
+    dim3 block(128), grid((P.g.nx + 127) / 128, k1 - k0 + 1);
+    k_wrap_y_phi<<<grid, block, 0, st>>>(P, k0, k1);
+    c->launches++;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sparse layout helpers
 // ---------------------------------------------------------------------------------------------------

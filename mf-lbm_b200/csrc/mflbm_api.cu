@@ -126,7 +126,9 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     if (cfg->struct_size != (int)sizeof(mflbm_config)) return fail(nullptr, MFLBM_ERR_ARG, "mflbm_config.struct_size mismatch");
     if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 2) return fail(nullptr, MFLBM_ERR_ARG, "bad lattice dimensions");
     if (cfg->npz < 1 || cfg->idz < 0 || cfg->idz >= cfg->npz) return fail(nullptr, MFLBM_ERR_ARG, "bad idz/npz");
-    if (cfg->jper != 0) return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) are not supported yet");
+    if (cfg->jper != 0 && cfg->npz != 1) return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) are supported on one z slab only (npz=1)");
+    if (cfg->jper != 0 && cfg->porous_plate_cmd != 0)
+        return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) need the sparse population layout, the porous plate the dense one");
     if (cfg->npz > 1 && !cfg->use_nccl) return fail(nullptr, MFLBM_ERR_ARG, "npz>1 requires use_nccl=1");
     if (cfg->npz > 1 && cfg->solver == MFLBM_SOLVER_MULTIPHASE && cfg->iz_async < 4)
         return fail(nullptr, MFLBM_ERR_ARG, "multiphase needs iz_async >= 4 (overlap_phi)");
@@ -223,6 +225,8 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         d.g.sx = (int)sx; d.g.sxy = (int)sxy; d.g.base = 16; d.g.ntot = (int)ntot;
         d.g.set_magic();
         d.multiphase = cfg->solver == MFLBM_SOLVER_MULTIPHASE;
+        d.jper = cfg->jper != 0;
+        d.kper = cfg->kper != 0;
         d.mrt = cfg->mrt;
         d.la_nui1 = cfg->la_nui1; d.la_nui2 = cfg->la_nui2; d.gamma = cfg->gamma; d.beta = cfg->beta;
         d.force_Z = cfg->force_Z; d.phi_inlet = cfg->phi_inlet; d.sa_inject = cfg->sa_inject;
@@ -354,7 +358,7 @@ struct HostActive {
 };
 
 static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i fastest */, HostActive &H, std::string &err,
-                             bool check) {
+                             bool check, bool jper = false, bool kper = false) {
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const long long bx = nx + 2, by = ny + 2, bz = nz + 2;  // 0..n+1 box
     auto W = [&](int i, int j, int k) -> int8_t {
@@ -398,6 +402,13 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
                 // independently of their images, MP/Init_multiphase.F90:276-311).
                 bool s = (k == 0 || k == nz + 1) && i >= 1 && i <= nx && j >= 1 && j <= ny && W(i, j, k) == 0;
                 for (int q = 1; q < 19 && !s; q++) s = isA(i + EX(q), j + EY(q), k + EZ(q));
+                // y-periodic: also the cells a fluid node reaches through the seam (same wrap rule as nbr_of below), so that
+                // the inlet / outlet kernels can address the image of a ghost-row cell by its cell index
+                if (jper && (kper || (k >= 1 && k <= nz)))
+                    for (int q = 1; q < 19 && !s; q++) {
+                        const int j2 = j + EY(q);
+                        if (j2 < 1 || j2 > ny) s = isA(i + EX(q), j2 < 1 ? j2 + ny : j2 - ny, k + EZ(q));
+                    }
                 if (s) {
                     idx[B(i, j, k)] = -2;
                     c++;
@@ -438,7 +449,15 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
         const unsigned r = (unsigned)(cellA[n] - (g.base - 4));
         const unsigned kz = r / (unsigned)g.sxy, r2 = r - kz * (unsigned)g.sxy;
         const unsigned jy = r2 / (unsigned)g.sx, ix = r2 - jy * (unsigned)g.sx;
-        return idx[B((int)ix - 3 + EX(q), (int)jy - 3 + EY(q), (int)kz - 3 + EZ(q))];
+        int j2 = (int)jy - 3 + EY(q);
+        const int k2 = (int)kz - 3 + EZ(q);
+        // y-periodic lattice (one process in y: the reference exchanges with itself, MP/Mpi.F90:147-207, :398-456): the
+        // neighbour across the seam IS the periodic image, so the y faces -- and, with z periodic too, the x edges, through the
+        // z ghost-plane cell of the image column, which k_wrap_z serves -- need no copies at all.  With z not periodic the
+        // reference exchanges rows k = 1..nz only: the ghost-plane cells behind the seam stay what the inlet / outlet
+        // routines make of them, and so they do here.
+        if (jper && (kper || (k2 >= 1 && k2 <= nz))) j2 = j2 < 1 ? j2 + ny : (j2 > ny ? j2 - ny : j2);
+        return idx[B((int)ix - 3 + EX(q), j2, k2)];
     };
     const bool stats = getenv("MFLBM_ADJ_STATS") != nullptr;  // developer: histogram of index runs per (warp, direction)
     long long hist[16] = {0};
@@ -563,7 +582,7 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
         std::string err;
         const char *e = getenv("MFLBM_CHECK_ADJ");
         const bool check = e ? atoi(e) != 0 : ((long long)nx * ny * nz <= 8000000LL);
-        if (build_active_host(g, walls, H, err, check)) return fail(ctx, MFLBM_ERR_ARG, err);
+        if (build_active_host(g, walls, H, err, check, d.jper != 0, d.kper != 0)) return fail(ctx, MFLBM_ERR_ARG, err);
     }
     ctx->kstartA = H.kstartA;
     for (int q = 0; q < 19; q++) d.nlink[q] = H.nlink[q];
@@ -640,6 +659,7 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     const mflbm_config &cfg = ctx->cfg;
     int variant = cfg.kernel_variant;  // 0 auto, 1 dense, 2 sparse
     if (cfg.porous_plate_cmd != 0) variant = 1;  // the porous plate copies from arbitrary (non-active) nodes
+    if (cfg.jper != 0) variant = 2;              // the y wrap of the populations is part of the adjacency (build_active_host)
     if (variant == 0) {
         long long fluid = 0;
 #pragma omp parallel for reduction(+ : fluid) schedule(static)
@@ -1121,6 +1141,7 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
         } else {
             if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
             if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);
+            if (cfg.jper == 1) launch_wrap_y_phi(ctx, s);  // after the z wrap: the x edges are images of images
         }
         CU(cudaEventRecord(ctx->ev_phi, s));  // nothing below writes phi at a fluid node (BC: ghost planes, K3: solid nodes)
         ctx->ev_phi_valid = true;

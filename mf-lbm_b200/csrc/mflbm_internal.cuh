@@ -167,6 +167,7 @@ struct Dev {
     int wq_stamp;            // stamp written by the last tile update (tile_stamp_warps, run by the K4 launch)
     int wq_all;              // 1: every warp counts as active (after a reset, until the next tile update)
     // scalars
+    int jper, kper;   // periodic indicators (jper: y wrap of the populations lives in the adjacency, phi by k_wrap_y_phi)
     int multiphase, mrt;
     double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
     double s_e, s_e2, s_q, s_nu, s_pi, s_t;
@@ -311,6 +312,7 @@ void launch_chain_early(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
 void launch_chain_late(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);
 void launch_wrap_z(mflbm_ctx *c, cudaStream_t st, bool push);
+void launch_wrap_y_phi(mflbm_ctx *c, cudaStream_t st);
 void launch_macro(mflbm_ctx *c, cudaStream_t st);
 void launch_monitor(mflbm_ctx *c, cudaStream_t st, double *out /*device, (10)*nz*/);
 int launch_saturation(mflbm_ctx *c, cudaStream_t st, double *out /*device, 2 rows of partial sums*/);

@@ -390,6 +390,16 @@ void Driver::set_walls() {  // MP/Misc.F90:6-210, pore_profile :298-365, transpo
                 if (c.kper == 1 || idz != 0) walls[w2(i, j, k - 2)] = G(i, j, idz * nz + (k - 2));
                 if (c.kper == 1 || idz != c.npz - 1) walls[w2(i, j, k + nz)] = G(i, j, idz * nz + nz + k);
             }
+    // ytransport_walls(0,2,2): y is never decomposed here, so a y-periodic lattice exchanges with itself
+    // (MP/Mpi_misc.F90:337-502, after the z transport: the z ghost planes take part)
+    if (c.jper == 1)
+        for (int k = -1; k <= nz + 2; k++)
+            for (int j = 1; j <= 2; j++)
+                for (int i = 1; i <= nx; i++) {
+                    const int8_t lo = walls[w2(i, j, k)], hi = walls[w2(i, ny + j - 2, k)];
+                    walls[w2(i, j - 2, k)] = hi;
+                    walls[w2(i, j + ny, k)] = lo;
+                }
 }
 
 namespace {

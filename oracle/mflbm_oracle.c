@@ -1320,6 +1320,84 @@ static void periodic_z_phi(orc_state *s) {
             }
 }
 
+/* y faces, self exchange of a y-periodic lattice (npy == 1): MP/Mpi.F90:147-180, :270-305 (pull), :398-430, :521-553 (push).
+ * Rows i = 1..nx, k = 1..nz only, exactly like the reference's buffers. */
+static void periodic_y_pdf(orc_state *s, int push) {
+    const int nx = s->nx, ny = s->ny, nz = s->nz, mp = s->p.multiphase;
+    static const int qM[5] = {4, 10, 9, 16, 18}; /* e_y = -1 */
+    static const int qP[5] = {3, 7, 8, 15, 17};  /* e_y = +1 */
+    for (int fl = 0; fl < (mp ? 2 : 1); fl++) {
+        double **F = fl == 0 ? s->f : s->g;
+        for (int m = 0; m < 5; m++)
+            for (int k = 1; k <= nz; k++)
+                for (int i = 1; i <= nx; i++) {
+                    if (!push) { /* own j=1 / j=ny rows -> yM / yP neighbour ghosts */
+                        F_(qM[m], i, ny + 1, k) = F_(qM[m], i, 1, k);
+                        F_(qP[m], i, 0, k) = F_(qP[m], i, ny, k);
+                    } else { /* own ghost rows -> neighbour interior rows */
+                        F_(qP[m], i, ny, k) = F_(qP[m], i, 0, k);
+                        F_(qM[m], i, 1, k) = F_(qM[m], i, ny + 1, k);
+                    }
+                }
+    }
+}
+
+/* edges along x when y AND z are exchanged (MP/Mpi.F90:184-207, :316-341 pull; :434-456, :566-590 push); applied after
+ * the faces ("face communication will contaminate edge communication") */
+static void periodic_yz_edges_pdf(orc_state *s, int push) {
+    const int nx = s->nx, ny = s->ny, nz = s->nz, mp = s->p.multiphase;
+    for (int fl = 0; fl < (mp ? 2 : 1); fl++) {
+        double **F = fl == 0 ? s->f : s->g;
+        for (int i = 1; i <= nx; i++) {
+            if (!push) {
+                F_(18, i, ny + 1, nz + 1) = F_(18, i, 1, 1);   /* send yMzM -> recv yPzP */
+                F_(16, i, ny + 1, 0) = F_(16, i, 1, nz);       /* send yMzP -> recv yPzM */
+                F_(17, i, 0, nz + 1) = F_(17, i, ny, 1);       /* send yPzM -> recv yMzP */
+                F_(15, i, 0, 0) = F_(15, i, ny, nz);           /* send yPzP -> recv yMzM */
+            } else {
+                F_(15, i, ny, nz) = F_(15, i, 0, 0);           /* send yMzM (ghost) -> recv yPzP */
+                F_(17, i, ny, 1) = F_(17, i, 0, nz + 1);       /* send yMzP -> recv yPzM */
+                F_(16, i, 1, nz) = F_(16, i, ny + 1, 0);       /* send yPzM -> recv yMzP */
+                F_(18, i, 1, 1) = F_(18, i, ny + 1, nz + 1);   /* send yPzP -> recv yMzM */
+            }
+        }
+    }
+}
+
+/* phi: y faces (k = 1..nz) and, with z periodic too, the four x edges (MP/Mpi.F90:633-655 pack, :729-790 update) */
+static void periodic_y_phi(orc_state *s, int with_z_edges) {
+    const int nx = s->nx, ny = s->ny, nz = s->nz;
+    for (int k = 1; k <= nz; k++)
+        for (int j = 1; j <= 4; j++)
+            for (int i = 1; i <= nx; i++) {
+                double lo = s->phi[I4(i, j, k)], hi = s->phi[I4(i, ny + j - 4, k)];
+                s->phi[I4(i, j - 4, k)] = hi;
+                s->phi[I4(i, j + ny, k)] = lo;
+            }
+    if (!with_z_edges) return;
+    for (int k = 1; k <= 4; k++)
+        for (int j = 1; j <= 4; j++)
+            for (int i = 1; i <= nx; i++) {
+                double mm = s->phi[I4(i, j, k)], pp = s->phi[I4(i, ny + j - 4, nz + k - 4)];
+                double mp_ = s->phi[I4(i, j, nz + k - 4)], pm = s->phi[I4(i, ny + j - 4, k)];
+                s->phi[I4(i, j - 4, k - 4)] = pp;    /* recv yMzM <- send yPzP */
+                s->phi[I4(i, j + ny, k - 4)] = mp_;  /* recv yPzM <- send yMzP */
+                s->phi[I4(i, j + ny, k + nz)] = mm;  /* recv yPzP <- send yMzM */
+                s->phi[I4(i, j - 4, k + nz)] = pm;   /* recv yMzP <- send yPzM */
+            }
+}
+
+static void periodic_exchange(orc_state *s, int push) {
+    const orc_params *p = &s->p;
+    if (p->kper == 1) periodic_z_pdf(s, push);
+    if (p->jper == 1) periodic_y_pdf(s, push);
+    if (p->kper == 1 && p->jper == 1) periodic_yz_edges_pdf(s, push);
+    if (p->multiphase) {
+        if (p->kper == 1) periodic_z_phi(s);
+        if (p->jper == 1) periodic_y_phi(s, p->kper == 1);
+    }
+}
+
 /* =====================================================================================
  * main_iteration_kernel, MP/Main_multiphase.F90:341-486 ; SP/Main.F90:291-422  (np == 1)
  * ===================================================================================== */
@@ -1327,16 +1405,13 @@ void orc_step(orc_state *s, int ntime) {
     const orc_params *p = &s->p;
     const int nx = s->nx, ny = s->ny, nz = s->nz;
     const int open_z = (p->kper == 0 && p->wsz0 == 0 && p->wsz1 == 0);
-    if (p->npz != 1 || p->jper != 0) {
-        fprintf(stderr, "oracle: orc_step supports np=1, jper=0 only\n");
+    if (p->npz != 1) {
+        fprintf(stderr, "oracle: orc_step supports np=1 only\n");
         abort();
     }
     if (ntime % 2 == 0) {
         orc_kernel_even(s, 1, nx, 1, ny, 1, nz);
-        if (p->kper == 1) {
-            periodic_z_pdf(s, 0);
-            if (p->multiphase) periodic_z_phi(s);
-        }
+        periodic_exchange(s, 0);
         if (open_z) {
             if (p->inlet_BC == 1) inlet_velocity(s, 0);
             else if (p->inlet_BC == 2) inlet_pressure(s, 0);
@@ -1346,10 +1421,7 @@ void orc_step(orc_state *s, int ntime) {
         if (p->multiphase && p->porous_plate_cmd != 0) porous_plate(s, 0);
     } else {
         orc_kernel_odd(s, 1, nx, 1, ny, 1, nz);
-        if (p->kper == 1) {
-            periodic_z_pdf(s, 1);
-            if (p->multiphase) periodic_z_phi(s);
-        }
+        periodic_exchange(s, 1);
         if (open_z) {
             if (p->inlet_BC == 1) inlet_velocity(s, 1);
             else if (p->inlet_BC == 2) inlet_pressure(s, 1);

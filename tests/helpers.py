@@ -95,6 +95,13 @@ def slot_mask(o, q):
         ex, ey, ez = EX[q], EY[q], EZ[q]
         src = a[max(0, ex):nx - max(0, -ex), max(0, ey):ny - max(0, -ey), max(0, ez):nz - max(0, -ez)]
         m[max(0, -ex):nx - max(0, ex), max(0, -ey):ny - max(0, ey), max(0, -ez):nz - max(0, ez)] |= src
+    if o.p.jper:
+        # y-periodic: the population storage of the y ghost rows is aliased to the periodic images (the exchange is part of
+        # the adjacency), so mflbm_download leaves those rows of the caller's arrays alone -- where z is exchanged too, and
+        # in the rows k = 1..nz otherwise (the reference exchanges no others, MP/Mpi.F90:147-180)
+        ks = slice(None) if o.p.kper else slice(1, -1)
+        m[:, 0, ks] = False
+        m[:, -1, ks] = False
     return m
 
 

@@ -203,3 +203,19 @@ def test_boundary_condition_setups_match_oracle(tmp_path, inlet, outlet):
     assert np.array_equal(d.field("w_in"), o.field("w_in"))
     assert np.array_equal(d.field("phi"), o.field("phi"))
     d.close()
+
+
+def test_y_periodic_setup_matches_oracle(tmp_path):
+    """reference test-suite case 1 shape (1.drop_attached_wall: y and z periodic, domain_wall_status_y = 0): walls incl. the
+    wrapped y ghost rows, boundary-node lists and the initial state"""
+    rng = np.random.default_rng(12)
+    wg = (rng.random((18, 16, 20)) < 0.15).astype(np.int8)
+    d = _driver(tmp_path, walls=wg, lattice_dimensions="18,16,20", periodic_indicator="0,1,1", domain_wall_status_y="0,0",
+                initial_fluid_distribution_option=3, initial_interface_position=6.0, theta=45, inlet_BC=0, outlet_BC=0,
+                excluded_layers="0,0")
+    o = make_oracle(nxG=18, nyG=16, nzG=20, jper=1, kper=1, wsy0=0, wsy1=0, walls_global=wg, initial_fluid_distribution_option=3,
+                    interface_z0=6.0, theta_deg=45.0, inlet_BC=0, outlet_BC=0, n_exclude_inlet=0, n_exclude_outlet=0)
+    assert np.array_equal(d.walls, o.walls)
+    _same_lists(d, o)
+    assert np.array_equal(d.field("phi"), o.field("phi"))
+    d.close()

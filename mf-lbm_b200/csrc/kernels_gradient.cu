@@ -290,7 +290,12 @@ __device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int sta
         const int ix = 8 * tx + (e & 7), jy = 4 * ty + ((e >> 3) & 3), kz = 4 * tz + (e >> 5);
         if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
         const int a = P.smap[P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz];
-        if (a >= 0 && a < P.nA) P.wstamp[a >> 5] = stamp;
+        // consecutive cells of a row are consecutive fluid nodes: one store per run of lanes with the same warp word
+        const int w = (a >= 0 && a < P.nA) ? (a >> 5) : -1;
+        const unsigned act = __activemask();
+        const int prev = __shfl_up_sync(act, w, 1);
+        const int lane = threadIdx.x & 31;
+        if (w >= 0 && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != w)) P.wstamp[w] = stamp;
     }
 }
 
@@ -340,6 +345,35 @@ __global__ void __launch_bounds__(128) k_gradient_tiles(const Dev P, int stamp) 
             }
         }
         __syncthreads();
+    }
+}
+
+// K4 on the active tiles WITHOUT lists: the 128 threads of a block own the 128 cells of one 8x4x4 tile and find out by
+// themselves whether their cell is a non-solid cell of the (-1:n+2)^3 box (walls) and which warp of fluid nodes it belongs
+// to (smap, for the stamp).  After the tile index every load of a thread -- wall flag, active index, the 19 phi values --
+// is independent of every other: one memory round trip, where the list version (k_chain_tiles<4>) chains tile index ->
+// CSR range -> cell list -> phi.  Lanes on solid cells idle, which does not matter to a latency-bound kernel.
+__global__ void __launch_bounds__(128) k_gradient_tiles_direct(const Dev P, int stamp, int force) {
+    if (!force && !P.tcount[3]) return;
+    const int count = P.tcount[0];
+    const int tid = threadIdx.x;
+    const int a = tid & 7, b = (tid >> 3) & 3, d = tid >> 5;
+    for (int t = blockIdx.x; t < count; t += gridDim.x) {
+        const int tile = P.tact[t];
+        const int tx = tile % P.ntx, ty = (tile / P.ntx) % P.nty, tz = tile / (P.ntx * P.nty);
+        const int ix = 8 * tx + a, jy = 4 * ty + b, kz = 4 * tz + d;  // padded coordinates (i+3, j+3, k+3)
+        if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
+        const int c = P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz;
+        if (stamp > 0) {
+            const int n = P.smap[c];
+            const int w = (n >= 0 && n < P.nA) ? (n >> 5) : -1;
+            const unsigned act = __activemask();
+            const int prev = __shfl_up_sync(act, w, 1);
+            const int lane = threadIdx.x & 31;
+            if (w >= 0 && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != w)) P.wstamp[w] = stamp;
+        }
+        const bool inbox = ix >= 2 && ix <= P.g.nx + 5 && jy >= 2 && jy <= P.g.ny + 5 && kz >= 2 && kz <= P.g.nz + 5;
+        if (inbox && P.walls[c] != 1) gradient_at<true>(P, c);
     }
 }
 
@@ -416,9 +450,14 @@ __global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
 __global__ void __launch_bounds__(256) k_gradient_pack(const Dev P, int all) {
     const int lane = threadIdx.x & 31;
     const int nW = (P.nA + 31) >> 5;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     if (!all && P.use_tiles && P.tcount[2]) return;  // k_gradient_pack_all did it
-    for (int w0 = gw * 32; w0 < nW; w0 += tw * 32) {
+    // every warp draws groups of 32 node-warps from a ticket counter: the groups in flight stay inside one moving window
+    // of the lattice (see k_gradient_pack_all), whatever the share of quiet warps in each group
+    for (;;) {
+        int w0 = 0;
+        if (lane == 0) w0 = atomicAdd(&P.tcount[9], 1) * 32;
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        if (w0 >= nW) return;
         unsigned m = 0xffffffffu;
         if (!all) m = __ballot_sync(0xffffffffu, w0 + lane < nW && P.wstamp[w0 + lane] == P.wq_stamp);
         else if (w0 + 32 > nW) m = nW - w0 >= 32 ? 0xffffffffu : ((1u << (nW - w0)) - 1u);
@@ -495,7 +534,7 @@ void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st) {
         cap = resident_grid(k_gradient_pack, 256);
         cap_all = resident_grid(k_gradient_pack_all, 256);
     }
-    cudaMemsetAsync(P.tcount + 8, 0, sizeof(int), st);  // ticket counter
+    cudaMemsetAsync(P.tcount + 8, 0, 2 * sizeof(int), st);  // ticket counters of the two kernels
     k_gradient_pack_all<<<std::min(cap_all, (P.nA + 255) / 256), 256, 0, st>>>(P, all);
     c->launches++;
     if (all) return;
@@ -573,7 +612,8 @@ static void launch_chain_kernels(mflbm_ctx *c, cudaStream_t st, bool tiles, bool
     }
     if (P.nG > 0) {
         if (tiles) {
-            if (P.k4_smem && !force) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
+            if (P.k4_smem == 1 && !force) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
+            else if (P.k4_smem == 2) k_gradient_tiles_direct<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp, f);
             else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, c->tile_stamp, f);
             n++;
         }

@@ -238,9 +238,11 @@ __global__ void __launch_bounds__(128) k_tile_static(const Dev P, const unsigned
 // halves of a speculative step (mflbm_api.cu step_impl); the whole lattice is (0, ntz - 1, 1).
 __global__ void k_tile_update(const Dev P, int cur, int stamp, int tz_lo, int tz_hi, int inside) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.ntiles) return;
+    __shared__ int s_cnt[4], s_base;
     const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
-    if ((tz >= tz_lo && tz <= tz_hi) != (inside != 0)) return;
+    const bool mine = t < P.ntiles && ((tz >= tz_lo && tz <= tz_hi) == (inside != 0));
+    bool active = false;
+    if (mine) {
     unsigned U = 0;
     for (int dz = -1; dz <= 1; dz++) {
         const int z = tz + dz;
@@ -261,8 +263,24 @@ __global__ void k_tile_update(const Dev P, int cur, int stamp, int tz_lo, int tz
     P.tU[cur][t] = (unsigned char)U;
     P.tquiet[t] = quiet ? 1 : 0;
     P.tcls[cur ^ 1][t] = 0;
-    if (quiet) return;
-    P.tact[atomicAdd(&P.tcount[0], 1)] = t;
+    active = !quiet;
+    }
+    // Ordered append: the active tiles of this block (128 consecutive tile indices) go to tact as one run in index order,
+    // one atomic per block.  With one atomic per tile the list came out scrambled, and the chain kernels, which walk it
+    // block by block, lost the L2 reuse between neighbouring tiles' phi / normal boxes.
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) s_cnt[wib] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tot = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+        s_base = tot ? atomicAdd(&P.tcount[0], tot) : 0;
+    }
+    __syncthreads();
+    if (!active) return;
+    int pos = s_base + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < wib; w++) pos += s_cnt[w];
+    P.tact[pos] = t;
     atomicMax(&P.tcount[5], P.ntz - tz);  // layer range of the active tiles (zero-initialised: min as ntz - tz, max as tz + 1)
     atomicMax(&P.tcount[6], tz + 1);
     for (int dz = -1; dz <= 1; dz++) {
@@ -290,12 +308,7 @@ __device__ __forceinline__ void tile_stamp_warps(const Dev &P, int tile, int sta
         const int ix = 8 * tx + (e & 7), jy = 4 * ty + ((e >> 3) & 3), kz = 4 * tz + (e >> 5);
         if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
         const int a = P.smap[P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz];
-        // consecutive cells of a row are consecutive fluid nodes: one store per run of lanes with the same warp word
-        const int w = (a >= 0 && a < P.nA) ? (a >> 5) : -1;
-        const unsigned act = __activemask();
-        const int prev = __shfl_up_sync(act, w, 1);
-        const int lane = threadIdx.x & 31;
-        if (w >= 0 && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != w)) P.wstamp[w] = stamp;
+        if (a >= 0 && a < P.nA) P.wstamp[a >> 5] = stamp;
     }
 }
 
@@ -348,35 +361,11 @@ __global__ void __launch_bounds__(128) k_gradient_tiles(const Dev P, int stamp) 
     }
 }
 
-// K4 on the active tiles WITHOUT lists: the 128 threads of a block own the 128 cells of one 8x4x4 tile and find out by
-// themselves whether their cell is a non-solid cell of the (-1:n+2)^3 box (walls) and which warp of fluid nodes it belongs
-// to (smap, for the stamp).  After the tile index every load of a thread -- wall flag, active index, the 19 phi values --
-// is independent of every other: one memory round trip, where the list version (k_chain_tiles<4>) chains tile index ->
-// CSR range -> cell list -> phi.  Lanes on solid cells idle, which does not matter to a latency-bound kernel.
-__global__ void __launch_bounds__(128) k_gradient_tiles_direct(const Dev P, int stamp, int force) {
-    if (!force && !P.tcount[3]) return;
-    const int count = P.tcount[0];
-    const int tid = threadIdx.x;
-    const int a = tid & 7, b = (tid >> 3) & 3, d = tid >> 5;
-    for (int t = blockIdx.x; t < count; t += gridDim.x) {
-        const int tile = P.tact[t];
-        const int tx = tile % P.ntx, ty = (tile / P.ntx) % P.nty, tz = tile / (P.ntx * P.nty);
-        const int ix = 8 * tx + a, jy = 4 * ty + b, kz = 4 * tz + d;  // padded coordinates (i+3, j+3, k+3)
-        if (jy >= P.g.ny + 8 || kz >= P.g.nz + 8) continue;
-        const int c = P.g.base - 4 + ix + P.g.sx * jy + P.g.sxy * kz;
-        if (stamp > 0) {
-            const int n = P.smap[c];
-            const int w = (n >= 0 && n < P.nA) ? (n >> 5) : -1;
-            const unsigned act = __activemask();
-            const int prev = __shfl_up_sync(act, w, 1);
-            const int lane = threadIdx.x & 31;
-            if (w >= 0 && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != w)) P.wstamp[w] = stamp;
-        }
-        const bool inbox = ix >= 2 && ix <= P.g.nx + 5 && jy >= 2 && jy <= P.g.ny + 5 && kz >= 2 && kz <= P.g.nz + 5;
-        if (inbox && P.walls[c] != 1) gradient_at<true>(P, c);
-    }
-}
-
+// MEASURED AND REJECTED (r02_k4, the 1536x1536x192 slab, 560 K active tiles): K4 on the active tiles without lists (one
+// thread per tile cell, wall flag / active index / 19 phi values all independent loads after the tile index): 993 us
+// against 992 us for k_chain_tiles<4>; neither deduplicating the warp-stamp stores (1025 us) nor appending the active
+// tiles in index order (1019 us) moves it.  The kernel is bound by fetching ~3.5 KB of scattered 80-byte phi rows per
+// tile, not by its dependent loads.
 // every tile active (explicit mflbm_color_gradient)
 __global__ void k_tile_all(const Dev P) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,7 +602,6 @@ static void launch_chain_kernels(mflbm_ctx *c, cudaStream_t st, bool tiles, bool
     if (P.nG > 0) {
         if (tiles) {
             if (P.k4_smem == 1 && !force) k_gradient_tiles<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp);
-            else if (P.k4_smem == 2) k_gradient_tiles_direct<<<P.ntiles < 148 * 16 ? P.ntiles : 148 * 16, 128, 0, st>>>(P, c->tile_stamp, f);
             else k_chain_tiles<4><<<grid, 64, 0, st>>>(P, c->tile_stamp, f);
             n++;
         }

@@ -673,9 +673,7 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     d.sparse = variant == 2;
     d.full_curv = variant == 1;
     d.use_tiles = (d.sparse && d.multiphase && !getenv("MFLBM_NO_TILES")) ? 1 : 0;
-    // K4 on active tiles: 0 = list gathers (k_chain_tiles<4>), 1 = phi staged through shared memory (measured slower,
-    // kernels_gradient.cu), 2 = list-free, one thread per tile cell (k_gradient_tiles_direct)
-    d.k4_smem = getenv("MFLBM_K4_SMEM") ? atoi(getenv("MFLBM_K4_SMEM")) : 0;
+    d.k4_smem = getenv("MFLBM_K4_SMEM") ? 1 : 0;  // measured slower than the list gathers (kernels_gradient.cu), off by default
     if (d.use_tiles) {
         d.ntx = g.sx / 8;
         d.nty = (g.ny + 8 + 3) / 4;

@@ -487,6 +487,10 @@ def parity_ngpu(rk, M, local_rank):
                             interface_z0=6.0, n_exclude_inlet=0, n_exclude_outlet=0),
         "sp_periodic": dict(multiphase=0, nxG=20, nyG=18, nzG=nzG, kper=1, force_z0=1e-5, la_nu1=0.1, n_exclude_inlet=0,
                             n_exclude_outlet=0),
+        "mp_yz_periodic": dict(nxG=20, nyG=18, nzG=nzG, jper=1, kper=1, wsy0=0, wsy1=0, inlet_BC=0, outlet_BC=0, force_z0=2e-4,
+                               la_nu2=0.04, initial_fluid_distribution_option=3, interface_z0=7.0, n_exclude_inlet=0, n_exclude_outlet=0),
+        "mp_y_periodic_open": dict(nxG=20, nyG=18, nzG=nzG, jper=1, wsy0=0, wsy1=0, la_nu2=0.04, interface_z0=6.0, n_exclude_inlet=0,
+                                   n_exclude_outlet=0),
     }
     steps = 9
     rng = np.random.default_rng(3)
@@ -495,7 +499,7 @@ def parity_ngpu(rk, M, local_rank):
     wg[:, :, -3:] = 0
     bad_total, names = 0, []
     for name in sorted(cases):
-        for layout in (2, 1):
+        for layout in ((2,) if cases[name].get("jper") else (2, 1)):  # y-periodic lattices always run the sparse layout
             ref = make_oracle(walls_global=wg, **cases[name])  # single domain
             if ref.mp:
                 ref.color_gradient()

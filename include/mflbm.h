@@ -57,8 +57,8 @@ typedef struct {
     int32_t nxGlobal, nyGlobal, nzGlobal;
     int32_t idz, npz;               /* slab position; x,y undivided (MP/IO_multiphase.F90:495-498) */
     int32_t jper, kper;             /* periodic indicators (x periodic is rejected by the reference).  jper = 1 (y is never
-                                       decomposed: the reference exchanges with itself, MP/Mpi.F90:22-40, :147-207): one z
-                                       slab only (npz = 1, else MFLBM_ERR_ARG), always the sparse population layout */
+                                       decomposed here: the lattice exchanges with itself in y, MP/Mpi.F90:22-40, :147-207;
+                                       z slabs are fine) always runs the sparse population layout */
     int32_t domain_wall_status_z_min, domain_wall_status_z_max;
     int32_t inlet_BC, outlet_BC;    /* 1 velocity / convective, 2 Zou-He pressure */
     int32_t porous_plate_cmd, Z_porous_plate;

@@ -332,7 +332,7 @@ __global__ void k_wrap_y_phi(const Dev P, int k0, int k1) {
 void launch_wrap_y_phi(mflbm_ctx *c, cudaStream_t st) {
     const Dev &P = c->d;
     if (!P.multiphase) return;
-    const int k0 = P.kper ? -3 : 1, k1 = P.kper ? P.g.nz + 4 : P.g.nz;
+    const int k0 = P.yw_lo ? -3 : 1, k1 = P.yw_hi ? P.g.nz + 4 : P.g.nz;
     dim3 block(128), grid((P.g.nx + 127) / 128, k1 - k0 + 1);
     k_wrap_y_phi<<<grid, block, 0, st>>>(P, k0, k1);
     c->launches++;

@@ -126,7 +126,6 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     if (cfg->struct_size != (int)sizeof(mflbm_config)) return fail(nullptr, MFLBM_ERR_ARG, "mflbm_config.struct_size mismatch");
     if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 2) return fail(nullptr, MFLBM_ERR_ARG, "bad lattice dimensions");
     if (cfg->npz < 1 || cfg->idz < 0 || cfg->idz >= cfg->npz) return fail(nullptr, MFLBM_ERR_ARG, "bad idz/npz");
-    if (cfg->jper != 0 && cfg->npz != 1) return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) are supported on one z slab only (npz=1)");
     if (cfg->jper != 0 && cfg->porous_plate_cmd != 0)
         return fail(nullptr, MFLBM_ERR_ARG, "y-periodic domains (jper=1) need the sparse population layout, the porous plate the dense one");
     if (cfg->npz > 1 && !cfg->use_nccl) return fail(nullptr, MFLBM_ERR_ARG, "npz>1 requires use_nccl=1");
@@ -227,6 +226,8 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
         d.multiphase = cfg->solver == MFLBM_SOLVER_MULTIPHASE;
         d.jper = cfg->jper != 0;
         d.kper = cfg->kper != 0;
+        d.yw_lo = d.jper && (cfg->kper != 0 || (cfg->npz > 1 && cfg->idz != 0));
+        d.yw_hi = d.jper && (cfg->kper != 0 || (cfg->npz > 1 && cfg->idz != cfg->npz - 1));
         d.mrt = cfg->mrt;
         d.la_nui1 = cfg->la_nui1; d.la_nui2 = cfg->la_nui2; d.gamma = cfg->gamma; d.beta = cfg->beta;
         d.force_Z = cfg->force_Z; d.phi_inlet = cfg->phi_inlet; d.sa_inject = cfg->sa_inject;
@@ -358,7 +359,7 @@ struct HostActive {
 };
 
 static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i fastest */, HostActive &H, std::string &err,
-                             bool check, bool jper = false, bool kper = false) {
+                             bool check, bool jper = false, bool yw_lo = false, bool yw_hi = false) {
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const long long bx = nx + 2, by = ny + 2, bz = nz + 2;  // 0..n+1 box
     auto W = [&](int i, int j, int k) -> int8_t {
@@ -404,7 +405,7 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
                 for (int q = 1; q < 19 && !s; q++) s = isA(i + EX(q), j + EY(q), k + EZ(q));
                 // y-periodic: also the cells a fluid node reaches through the seam (same wrap rule as nbr_of below), so that
                 // the inlet / outlet kernels can address the image of a ghost-row cell by its cell index
-                if (jper && (kper || (k >= 1 && k <= nz)))
+                if (jper && ((k >= 1 && k <= nz) || (k < 1 && yw_lo) || (k > nz && yw_hi)))
                     for (int q = 1; q < 19 && !s; q++) {
                         const int j2 = j + EY(q);
                         if (j2 < 1 || j2 > ny) s = isA(i + EX(q), j2 < 1 ? j2 + ny : j2 - ny, k + EZ(q));
@@ -453,10 +454,10 @@ static int build_active_host(const Grid &g, const int8_t *walls /* (-1:n+2)^3, i
         const int k2 = (int)kz - 3 + EZ(q);
         // y-periodic lattice (one process in y: the reference exchanges with itself, MP/Mpi.F90:147-207, :398-456): the
         // neighbour across the seam IS the periodic image, so the y faces -- and, with z periodic too, the x edges, through the
-        // z ghost-plane cell of the image column, which k_wrap_z serves -- need no copies at all.  With z not periodic the
-        // reference exchanges rows k = 1..nz only: the ghost-plane cells behind the seam stay what the inlet / outlet
-        // routines make of them, and so they do here.
-        if (jper && (kper || (k2 >= 1 && k2 <= nz))) j2 = j2 < 1 ? j2 + ny : (j2 > ny ? j2 - ny : j2);
+        // z ghost-plane cell of the image column, which k_wrap_z / the halo exchange with the neighbour slab serves -- need
+        // no copies at all.  At an open end of the lattice the reference exchanges rows k = 1..nz only: the ghost-plane cells
+        // behind the seam stay what the inlet / outlet routines make of them, and so they do here.
+        if (jper && ((k2 >= 1 && k2 <= nz) || (k2 < 1 && yw_lo) || (k2 > nz && yw_hi))) j2 = j2 < 1 ? j2 + ny : (j2 > ny ? j2 - ny : j2);
         return idx[B((int)ix - 3 + EX(q), j2, k2)];
     };
     const bool stats = getenv("MFLBM_ADJ_STATS") != nullptr;  // developer: histogram of index runs per (warp, direction)
@@ -582,7 +583,7 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
         std::string err;
         const char *e = getenv("MFLBM_CHECK_ADJ");
         const bool check = e ? atoi(e) != 0 : ((long long)nx * ny * nz <= 8000000LL);
-        if (build_active_host(g, walls, H, err, check, d.jper != 0, d.kper != 0)) return fail(ctx, MFLBM_ERR_ARG, err);
+        if (build_active_host(g, walls, H, err, check, d.jper != 0, d.yw_lo != 0, d.yw_hi != 0)) return fail(ctx, MFLBM_ERR_ARG, err);
     }
     ctx->kstartA = H.kstartA;
     for (int q = 0; q < 19; q++) d.nlink[q] = H.nlink[q];
@@ -1042,7 +1043,7 @@ static SpecPlan spec_plan(mflbm_ctx *ctx) {
     SpecPlan p{false, 0, 0, 0, 0};
     const Dev &d = ctx->d;
     const mflbm_config &cfg = ctx->cfg;
-    if (!ctx->spec_enabled || !d.multiphase || !d.sparse || !d.use_tiles || d.wq_all) return p;
+    if (!ctx->spec_enabled || !d.multiphase || !d.sparse || !d.use_tiles || d.wq_all || d.jper) return p;
     int force_lo = -1, force_hi = -1;
     if (const char *f = getenv("MFLBM_SPEC_FORCE"))  // test knob "lo:hi": pretend the active tiles are in these layers
         sscanf(f, "%d:%d", &force_lo, &force_hi);
@@ -1138,6 +1139,7 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
             CU(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
             if (collide_timed(ctx, s, odd, iz + 1, nz - iz)) return MFLBM_ERR_CUDA;
             CU(cudaStreamWaitEvent(s, ctx->ev_halo, 0));
+            if (cfg.jper == 1) launch_wrap_y_phi(ctx, s);  // after the halo planes arrived: covers the x edges
         } else {
             if (collide_timed(ctx, s, odd, 1, nz)) return MFLBM_ERR_CUDA;
             if (cfg.kper == 1) launch_wrap_z(ctx, s, odd);

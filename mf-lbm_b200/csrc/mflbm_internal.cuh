@@ -168,6 +168,8 @@ struct Dev {
     int wq_all;              // 1: every warp counts as active (after a reset, until the next tile update)
     // scalars
     int jper, kper;   // periodic indicators (jper: y wrap of the populations lives in the adjacency, phi by k_wrap_y_phi)
+    int yw_lo, yw_hi; // y-periodic: the z ghost planes below k=1 / above k=nz are exchanged (periodic wrap or neighbour slab),
+                      // so the y wrap applies to them too (the reference's x-edge exchange, MP/Mpi.F90:184-207, :656-670)
     int multiphase, mrt;
     double la_nui1, la_nui2, gamma, beta, force_Z, phi_inlet, sa_inject, relaxation, uin_avg, rho_in, rho_out;
     double s_e, s_e2, s_q, s_nu, s_pi, s_t;

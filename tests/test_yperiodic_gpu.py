@@ -75,9 +75,9 @@ def test_singlephase_y_periodic(kper):
     ctx.close()
 
 
-def test_y_periodic_is_refused_on_several_slabs():
+def test_y_periodic_with_the_porous_plate_is_refused():
     with pytest.raises(M.MflbmError, match="jper"):
-        M.Context(solver=1, nx=8, ny=8, nz=8, npz=2, idz=0, jper=1, use_nccl=1, iz_async=4)
+        M.Context(solver=1, nx=8, ny=8, nz=8, jper=1, porous_plate_cmd=1, Z_porous_plate=4)
 
 
 def test_reference_case1_drop_attached_to_the_wall():

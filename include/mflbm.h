@@ -155,6 +155,16 @@ int mflbm_profile_read(mflbm_ctx *ctx, double *collide_ms, long long *collide_la
  * many of them the last gradient chain skipped because phi is uniform around them.  Informational (bench.py reports
  * the fraction; tests use it to make sure the skipping path is exercised); 0/0 when the layout has no tiles. */
 int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nquiet);
+/* Which kernels evaluate color_gradient (MP/Phase_gradient.F90:5-265) on this context: *fused = 1 when the single fused
+ * kernel of the sparse multiphase layout is in use (csrc/march.cuh), 0 for the five reference-order kernels.  The fused
+ * kernel needs node lists as the reference's geometry_preprocessing_new makes them (every node listed once, on a cell of
+ * its kind, la_weight = sum of the listed neighbours' weights); *reject_mask says what was found otherwise
+ * (1 solid entry misplaced / duplicated, 2 foreign la_weight, 4 fluid entry misplaced / duplicated). */
+int mflbm_chain_info(mflbm_ctx *ctx, int *fused, int *reject_mask);
+/* Developer check: re-evaluates color_gradient on the current phase field with the five reference-order kernels and counts
+ * the entries of the packed colour gradient the collision kernel reads that differ bit for bit from what the last
+ * evaluation left there (0 expected; only meaningful right after mflbm_step / mflbm_color_gradient). */
+int mflbm_chain_selfcheck(mflbm_ctx *ctx, long long *mismatches);
 
 /* kernel launches issued by this context since create (bench.py "gpu_launches") */
 long long mflbm_launch_count(const mflbm_ctx *ctx);

@@ -49,7 +49,7 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
            "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
-           "mflbm_tile_stats", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
+           "mflbm_tile_stats", "mflbm_chain_info", "mflbm_chain_selfcheck", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
            "mflbm_output_begin", "mflbm_output_end", "mflbm_checkpoint_begin", "mflbm_checkpoint_fetch", "mflbm_checkpoint_end")
 
 
@@ -110,6 +110,8 @@ def load(strict=False):
     lib.mflbm_profile.argtypes = [vp, C.c_int]
     lib.mflbm_profile_read.argtypes = [vp, _DP, C.POINTER(C.c_longlong)]
     lib.mflbm_tile_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.mflbm_chain_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mflbm_chain_selfcheck.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.mflbm_launch_count.argtypes = [vp]
     lib.mflbm_launch_count.restype = C.c_longlong
     lib.mflbm_device_bytes.argtypes = [vp]
@@ -397,6 +399,18 @@ class Context:
         a, b = C.c_longlong(), C.c_longlong()
         self._chk(self.lib.mflbm_tile_stats(self.h, C.byref(a), C.byref(b)), "mflbm_tile_stats")
         return a.value, b.value
+
+    def chain_info(self):
+        """(fused, reject_mask): whether color_gradient runs as the single fused kernel (csrc/march.cuh), and why not"""
+        a, b = C.c_int(), C.c_int()
+        self._chk(self.lib.mflbm_chain_info(self.h, C.byref(a), C.byref(b)), "mflbm_chain_info")
+        return a.value, b.value
+
+    def chain_selfcheck(self):
+        """entries of the packed colour gradient that differ from a re-evaluation with the reference-order kernels"""
+        n = C.c_longlong()
+        self._chk(self.lib.mflbm_chain_selfcheck(self.h, C.byref(n)), "mflbm_chain_selfcheck")
+        return n.value
 
     @property
     def launch_count(self):

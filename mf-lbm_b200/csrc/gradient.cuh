@@ -25,6 +25,7 @@ __device__ __forceinline__ double ddz(F v) {
            MFLBM_ISO4_2 * (v(1, 0, 1) - v(-1, 0, -1) + v(-1, 0, 1) - v(1, 0, -1) + v(0, 1, 1) - v(0, -1, -1) + v(0, -1, 1) - v(0, 1, -1));
 }
 
+#ifndef MARCH_EMU  // (the CPU emulation of march.cuh only needs the derivative templates above)
 // The 19 stencil values of one field around cell c, ALL loaded before the first use.  The ISO4 sums are sequential
 // dependency chains in the reference's term order; written as "load where used", ptxas keeps few registers and issues the
 // loads in dependent batches (measured, r02 ncu: K4 / K7 kernels latency-bound at 25 % issue utilisation with every memory
@@ -66,5 +67,7 @@ __device__ __forceinline__ double curvature_at(const Dev &P, int c) {
     return (nx_ * nx_ - 1.0) * kxx + (ny_ * ny_ - 1.0) * kyy + (nz_ * nz_ - 1.0) * kzz + nx_ * ny_ * (kxy + kyx) +
            nx_ * nz_ * (kxz + kzx) + ny_ * nz_ * (kzy + kyz);
 }
+
+#endif  // MARCH_EMU
 
 }  // namespace mflbm

@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(128) k_gradient(const Dev P) {
 }
 
 // traversal of the list of non-solid cells of the same box (sparse layout: work scales with the pore space)
+template <bool LAZY>
 __global__ void __launch_bounds__(128) k_gradient_list(const Dev P) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < P.nG) gradient_at<true>(P, P.gcell[n]);
+    if (n < P.nG) gradient_at<LAZY>(P, P.gcell[n]);
 }
 
 __global__ void k_alter(const Dev P) {
@@ -281,6 +282,20 @@ __global__ void k_tile_update(const Dev P, int cur, int stamp, int tz_lo, int tz
     int pos = s_base + __popc(bal & ((1u << lane) - 1u));
     for (int w = 0; w < wib; w++) pos += s_cnt[w];
     P.tact[pos] = t;
+    if (P.mlist) {
+        // march kernel: every (column, chunk) work item that holds a cell of 1..n of this tile (tile cells in lattice
+        // coordinates: i = 8 tx - 3 .. 8 tx + 4, j = 4 ty - 3 .. 4 ty, k = 4 tz - 3 .. 4 tz), once per step
+        const int ia = max(1, 8 * tx - 3), ib = min(P.g.nx, 8 * tx + 4);
+        const int ja = max(1, 4 * ty - 3), jb = min(P.g.ny, 4 * ty);
+        const int ka = max(1, 4 * tz - 3), kb = min(P.g.nz, 4 * tz);
+        if (ia <= ib && ja <= jb && ka <= kb)
+            for (int bz = (ka - 1) / P.march_lz; bz <= (kb - 1) / P.march_lz; bz++)
+                for (int by = (ja - 1) / MFLBM_MARCH_TY; by <= (jb - 1) / MFLBM_MARCH_TY; by++)
+                    for (int bx = (ia - 1) / MFLBM_MARCH_TX; bx <= (ib - 1) / MFLBM_MARCH_TX; bx++) {
+                        const int item = bx + P.mcols_x * (by + P.mcols_y * bz);
+                        if (atomicExch(&P.mflag[item], stamp) != stamp) P.mlist[atomicAdd(&P.tcount[10], 1)] = item;
+                    }
+    }
     atomicMax(&P.tcount[5], P.ntz - tz);  // layer range of the active tiles (zero-initialised: min as ntz - tz, max as tz + 1)
     atomicMax(&P.tcount[6], tz + 1);
     for (int dz = -1; dz <= 1; dz++) {
@@ -491,7 +506,10 @@ static int resident_grid(K kernel, int block) {
 // few microseconds instead of one empty block per chunk (measured: 117 us on C3, 0.6 ns per block).  The grid-stride
 // scan above lets blocks drift apart over its ~170 iterations: 13.7 GB DRAM reads for 4.5 GB of operands on C3 with random
 // phi, every plane fetched three times (r02 ncu).  force = 0: runs only when the chain of this step swept every tile.
-__global__ void __launch_bounds__(256, 3) k_gradient_pack_all(const Dev P, int force) {
+#ifndef MFLBM_PACK_MINB
+#define MFLBM_PACK_MINB 3  // resident 256-thread blocks per SM the register allocation is bounded for (3 -> 80 registers; 2, 4, 5 measured slower: r02_pack)
+#endif
+__global__ void __launch_bounds__(256, MFLBM_PACK_MINB) k_gradient_pack_all(const Dev P, int force) {
     if (!force && !P.tcount[2]) return;
     __shared__ int s_chunk;
     const int nchunk = (P.nA + 255) >> 8;
@@ -650,9 +668,81 @@ void launch_chain_late(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi) {
     launch_gradient_pack(c, st);
 }
 
+// The reference-order chain K3..K6 over the whole lists into the DENSE arrays (phi on every listed solid node, n and
+// |grad phi| everywhere), whatever they held before: contexts that run the march kernel keep these arrays only for the
+// callers that ask for them (mflbm_download of the normals / the curvature, compute_macro_vars).
+void launch_dense_gradient(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.multiphase || !P.sparse || c->cn_dense_valid) return;
+    if (P.num_solid > 0) k_phi_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
+    if (P.nG > 0) k_gradient_list<false><<<(P.nG + 127) / 128, 128, 0, st>>>(P);
+    if (P.num_fluid > 0) k_alter<<<(P.num_fluid + 127) / 128, 128, 0, st>>>(P);
+    if (P.num_solid > 0) k_cn_solid<<<(P.num_solid + 127) / 128, 128, 0, st>>>(P);
+    c->launches += 4;
+    c->solid_phi_stale = false;
+    c->cn_dense_valid = true;
+}
+
+// Self-check of the march kernel against the list kernels on the current state: evaluates the reference-order chain into
+// the dense arrays, packs it into scratch buffers and counts the entries of G that differ bit for bit (0 = identical).
+__global__ void k_count_diff(const unsigned long long *a, const unsigned long long *b, int n, unsigned long long *out) {
+    unsigned long long bad = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) bad += a[e] != b[e];
+    if (bad) atomicAdd(out, bad);
+}
+
+long long chain_selfcheck(mflbm_ctx *c, cudaStream_t st) {
+    const Dev &P = c->d;
+    if (!P.multiphase || !P.sparse || P.nA <= 0) return 0;
+    c->cn_dense_valid = false;
+    launch_dense_gradient(c, st);
+    Dev Q = P;
+    double *scratch = nullptr;
+    unsigned long long *cnt = nullptr;
+    if (cudaMalloc((void **)&scratch, (size_t)4 * P.nA * sizeof(double)) != cudaSuccess) return -1;
+    if (cudaMalloc((void **)&cnt, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(scratch); return -1; }
+    for (int m = 0; m < 4; m++) Q.G[m] = scratch + (size_t)m * P.nA;
+    cudaMemsetAsync(P.tcount + 8, 0, 2 * sizeof(int), st);
+    cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st);
+    k_gradient_pack_all<<<std::min(resident_grid(k_gradient_pack_all, 256), (P.nA + 255) / 256), 256, 0, st>>>(Q, 1);
+    for (int m = 0; m < 4; m++)
+        k_count_diff<<<1024, 256, 0, st>>>((const unsigned long long *)P.G[m], (const unsigned long long *)Q.G[m], P.nA, cnt);
+    c->launches += 5;
+    unsigned long long h = 0;
+    const bool ok = cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+    cudaFree(scratch);
+    cudaFree(cnt);
+    return ok ? (long long)h : -1;
+}
+
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
     Dev &P = c->d;
     if (!P.multiphase) return;
+    if (c->march_on && c->march_ready) {
+        // one kernel (march.cuh); phi on the solid nodes and the dense normal arrays are not written
+        c->solid_phi_stale = true;
+        c->cn_dense_valid = false;
+        cudaMemsetAsync(P.tcount, 0, 12 * sizeof(int), st);
+        if (P.use_tiles && stepping) {
+            const int nb = (P.ntiles + 127) / 128;
+            k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp, 0, P.ntz - 1, 1);
+            k_tile_mode<<<1, 1, 0, st>>>(P, 0);
+            c->launches += 2;
+            P.wq_stamp = c->tile_stamp;
+            P.wq_all = 0;
+            P.tile_cur ^= 1;
+            launch_march(c, st, 1, 0);                 // most tiles active: everything
+            launch_march(c, st, 2, c->tile_stamp);     // else: the work items around the active tiles
+        } else {
+            if (P.use_tiles) {
+                launch_tiles_reset(c, st);
+                k_tile_all<<<(P.ntiles + 127) / 128, 128, 0, st>>>(P);
+                c->launches++;
+            }
+            launch_march(c, st, 0, 0);
+        }
+        return;
+    }
     if (P.use_tiles) {
         const int nb = (P.ntiles + 127) / 128;
         if (stepping) {
@@ -681,7 +771,7 @@ void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
     c->solid_phi_stale = false;
     if (P.sparse) {
         if (P.nG > 0) {
-            k_gradient_list<<<(P.nG + 127) / 128, 128, 0, st>>>(P);
+            k_gradient_list<true><<<(P.nG + 127) / 128, 128, 0, st>>>(P);
             c->launches++;
         }
     } else {

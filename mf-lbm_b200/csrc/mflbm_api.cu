@@ -151,6 +151,12 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->pdf_alloc = false;
     ctx->tiles_static_ready = false;
     ctx->solid_phi_stale = false;
+    // fused colour-gradient chain (kernels_march.cu) on the sparse multiphase layout; MFLBM_MARCH=0 keeps the list kernels
+    ctx->march_on = !(getenv("MFLBM_MARCH") && atoi(getenv("MFLBM_MARCH")) == 0);
+    ctx->march_ready = false;
+    ctx->march_reject = 0;
+    ctx->march_lz_flat = getenv("MFLBM_MARCH_LZ") ? std::max(1, atoi(getenv("MFLBM_MARCH_LZ"))) : 64;
+    ctx->cn_dense_valid = true;
     ctx->tile_stamp = 0;
     ctx->prof = false;
     ctx->prof_used = 0;
@@ -707,6 +713,19 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
     if (d.sparse && d.multiphase)
         for (int m = 0; m < 4; m++)
             if (dev_alloc(ctx, &d.G[m], (size_t)d.nA + 64)) return MFLBM_ERR_CUDA;
+    if (!(d.sparse && d.multiphase)) ctx->march_on = false;
+    if (ctx->march_on) {
+        d.mcols_x = (g.nx + MFLBM_MARCH_TX - 1) / MFLBM_MARCH_TX;
+        d.mcols_y = (g.ny + MFLBM_MARCH_TY - 1) / MFLBM_MARCH_TY;
+        d.march_lz = getenv("MFLBM_MARCH_LZR") ? std::max(1, atoi(getenv("MFLBM_MARCH_LZR"))) : 16;
+        d.mchunks = (g.nz + d.march_lz - 1) / d.march_lz;
+        if (dev_alloc(ctx, &d.mcode, (size_t)g.ntot, false)) return MFLBM_ERR_CUDA;
+        if (d.use_tiles) {
+            const size_t ni = (size_t)d.mcols_x * d.mcols_y * d.mchunks;
+            if (dev_alloc(ctx, &d.mflag, ni) || dev_alloc(ctx, &d.mlist, ni)) return MFLBM_ERR_CUDA;
+        }
+        ctx->march_ready = false;
+    }
     ctx->pdf_alloc = true;
     return 0;
 }
@@ -799,6 +818,7 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
         if (d.multiphase && xfer_pdf(ctx, d.gg[q], h->g[q], true, q)) return MFLBM_ERR_CUDA;
     }
     if (h->walls || h->phi || h->solid_boundary_nodes) ctx->tiles_static_ready = false;  // quiet-tile state restarts
+    if (h->walls || h->solid_boundary_nodes || h->fluid_boundary_nodes) ctx->march_ready = false;  // cell codes of the march kernel
     if (d.multiphase) {
         if (xfer(ctx, d.phi, h->phi, 4, nz + 8, -3, true)) return MFLBM_ERR_CUDA;
         if (h->phi_old) {
@@ -896,6 +916,10 @@ extern "C" int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *h) {
     if (d.multiphase) {
         if (h->phi && ctx->solid_phi_stale) {  // K3 was skipped on quiet tiles: give the caller the reference's values
             launch_phi_solid_refresh(ctx, ctx->s_main);
+            CU(cudaGetLastError());
+        }
+        if (d.sparse && (h->cn_x || h->cn_y || h->cn_z || h->c_norm || h->curv)) {  // march kernel: the dense arrays on demand
+            launch_dense_gradient(ctx, ctx->s_main);
             CU(cudaGetLastError());
         }
         if (d.sparse && h->curv) {  // not maintained per step on the sparse layout: evaluate K7 now (fluid nodes)
@@ -1043,7 +1067,7 @@ static SpecPlan spec_plan(mflbm_ctx *ctx) {
     SpecPlan p{false, 0, 0, 0, 0};
     const Dev &d = ctx->d;
     const mflbm_config &cfg = ctx->cfg;
-    if (!ctx->spec_enabled || !d.multiphase || !d.sparse || !d.use_tiles || d.wq_all || d.jper) return p;
+    if (!ctx->spec_enabled || !d.multiphase || !d.sparse || !d.use_tiles || d.wq_all || d.jper || ctx->march_on) return p;
     int force_lo = -1, force_hi = -1;
     if (const char *f = getenv("MFLBM_SPEC_FORCE"))  // test knob "lo:hi": pretend the active tiles are in these layers
         sscanf(f, "%d:%d", &force_lo, &force_hi);
@@ -1087,6 +1111,7 @@ static int step_impl(mflbm_ctx *ctx, int ntime) {
     const bool odd = (ntime % 2) != 0;
     cudaStream_t s = ctx->s_main;
     if (tiles_prepare(ctx, s)) return fail(ctx, MFLBM_ERR_CUDA, "quiet-tile setup failed");
+    if (march_prepare(ctx, s) < 0) return fail(ctx, MFLBM_ERR_CUDA, "march kernel setup failed");
     const SpecPlan sp = spec_plan(ctx);
     ctx->step_count++;
     const int iz = cfg.iz_async > 0 ? cfg.iz_async : 1;
@@ -1183,6 +1208,7 @@ extern "C" int mflbm_color_gradient(mflbm_ctx *ctx) {
     if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
     CU(cudaSetDevice(ctx->device));
     if (tiles_prepare(ctx, ctx->s_main)) return fail(ctx, MFLBM_ERR_CUDA, "quiet-tile setup failed");
+    if (march_prepare(ctx, ctx->s_main) < 0) return fail(ctx, MFLBM_ERR_CUDA, "march kernel setup failed");
     launch_color_gradient(ctx, ctx->s_main, false);
     return check_launch(ctx);
 }
@@ -1193,6 +1219,7 @@ extern "C" int mflbm_compute_macro_vars(mflbm_ctx *ctx) {
     if (ensure_macro(ctx)) return MFLBM_ERR_CUDA;
     // phi on solid nodes of 1..n is zeroed below (MP/Misc.F90:424); the listed solid nodes outside 1..n keep the last
     // K3 value, so refresh the ones quiet tiles skipped first, and let the next gradient chain evaluate every tile
+    if (ctx->d.sparse && ctx->d.multiphase) launch_dense_gradient(ctx, ctx->s_main);  // the CSF force term reads n, |grad phi|
     if (ctx->solid_phi_stale) launch_phi_solid_refresh(ctx, ctx->s_main);
     launch_macro(ctx, ctx->s_main);
     launch_tiles_reset(ctx, ctx->s_main);
@@ -1554,6 +1581,25 @@ extern "C" int mflbm_tile_stats(mflbm_ctx *ctx, long long *ntiles, long long *nq
     *ntiles = ctx->d.ntiles;
     *nquiet = q;
     return MFLBM_OK;
+}
+
+extern "C" int mflbm_chain_info(mflbm_ctx *ctx, int *fused, int *reject_mask) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->pdf_alloc && march_prepare(ctx, ctx->s_main) < 0) return fail(ctx, MFLBM_ERR_CUDA, "march kernel setup failed");
+    if (fused) *fused = (ctx->march_on && ctx->march_ready) ? 1 : 0;
+    if (reject_mask) *reject_mask = ctx->march_reject;
+    return MFLBM_OK;
+}
+
+extern "C" int mflbm_chain_selfcheck(mflbm_ctx *ctx, long long *mismatches) {
+    if (!ctx || !mismatches) return fail(ctx, MFLBM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_chain_selfcheck before mflbm_upload");
+    const long long r = chain_selfcheck(ctx, ctx->s_main);
+    if (r < 0) return fail(ctx, MFLBM_ERR_CUDA, "self-check of the colour-gradient chain failed to run");
+    *mismatches = r;
+    return check_launch(ctx);
 }
 
 extern "C" long long mflbm_launch_count(const mflbm_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -164,6 +164,13 @@ struct Dev {
     // The collision kernel reads this one warp-uniform word (address known from n alone) instead of chaining
     // cellA -> tile index -> tquiet -> c_norm; a warp whose stamp is stale skips the c_norm read altogether.
     int *wstamp;             // [ceil(nA/32)]
+    // march kernel (march.cuh): one code word per cell of the padded grid (type + neighbour mask / fluid-list index), and
+    // per (column, chunk of march_lz planes) the stamp of the last tile update that found an active tile there
+    unsigned *mcode;         // [ntot]
+    int *mflag;              // [mcols_x * mcols_y * mchunks]
+    int *mlist;              // work items (column + mcols_x * mcols_y * chunk) holding an active tile, appended by the tile
+                             // update (tcount[10] of them; tcount[11] is the ticket counter of the march kernel)
+    int mcols_x, mcols_y, mchunks, march_lz;
     int wq_stamp;            // stamp written by the last tile update (tile_stamp_warps, run by the K4 launch)
     int wq_all;              // 1: every warp counts as active (after a reset, until the next tile update)
     // scalars
@@ -191,6 +198,8 @@ __device__ __forceinline__ void tile_record(const Dev &P, int c, double phi) {
 }
 #endif
 
+#define MFLBM_MARCH_TX 32  // column of cells one block of the march kernel owns (march.cuh)
+#define MFLBM_MARCH_TY 16
 #define MFLBM_ADJ_REC 37  // uint4 records per warp
 #define MFLBM_SAT_SEG 4   // blocks per z slice of k_saturation (2 * nz * MFLBM_SAT_SEG partial sums fit red_len)
 
@@ -285,6 +294,12 @@ struct mflbm_ctx {
     bool open_z;
     bool macro_alloc;
     bool pdf_alloc;
+    // march kernel (kernels_march.cu): fused colour-gradient chain of the sparse multiphase layout
+    bool march_on;            // selected for this context (MFLBM_MARCH=0 keeps the list kernels)
+    bool march_ready;         // cell codes built for the current walls / node lists
+    int march_reject;         // why the node lists were not accepted (bit mask, 0 = accepted)
+    int march_lz_flat;        // planes per work item of the sweeps over everything
+    bool cn_dense_valid;      // the dense n / |grad phi| arrays hold the current values (the march kernel does not write them)
     int tile_stamp;
     bool tiles_static_ready;  // tstat computed for the current phi / wall / node-list upload
     bool solid_phi_stale;     // phi on solid boundary nodes of quiet tiles was not refreshed by the last gradient chain
@@ -310,6 +325,10 @@ void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);
 int tiles_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_curvature(mflbm_ctx *c, cudaStream_t st);
 void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st);
+int march_prepare(mflbm_ctx *c, cudaStream_t st);
+void launch_march(mflbm_ctx *c, cudaStream_t st, int mode, int stamp);
+void launch_dense_gradient(mflbm_ctx *c, cudaStream_t st);
+long long chain_selfcheck(mflbm_ctx *c, cudaStream_t st);
 void launch_chain_early(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
 void launch_chain_late(mflbm_ctx *c, cudaStream_t st, int tz_lo, int tz_hi);
 void launch_bc(mflbm_ctx *c, cudaStream_t st, bool after_odd);

@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--host-geometry", action="store_true",
                     help="run geometry_preprocessing_new on the host cores (default: on this rank's GPU, mflbm_geometry_preprocess)")
     ap.add_argument("--no-e2e", action="store_true", help="developer sweeps: skip the end-to-end leg (the line then has e2e = null)")
+    ap.add_argument("--e2e-blocking", action="store_true", help="e2e leg with mflbm_upload + mflbm_step + mflbm_cal_saturation (three "
+                    "blocking calls per step) instead of mflbm_step_streamed")
     ap.add_argument("--state", default="drainage", choices=["drainage", "random"],
                     help="developer / profiling: 'random' re-initialises with the seeded option-6 phase field BEFORE the headline region")
     ap.add_argument("--no-active", action="store_true", help="skip the interface-rich second timed regions (roofline_active = null)")
@@ -392,21 +394,33 @@ def main():
     t0 = time.perf_counter()
     drv.timer_start()
     acc = 0.0
-    for t in range(1, e2e_steps + 1):
-        drv.upload_w_in(w_in.data_ptr())
-        drv.main_iteration_kernel(t)
-        if mp:
-            v1, v2 = drv.cal_saturation_parts()
-            acc += v1
-        else:
-            drv.sync()
+    if args.e2e_blocking:  # round-1 form: three blocking calls per step
+        for t in range(1, e2e_steps + 1):
+            drv.upload_w_in(w_in.data_ptr())
+            drv.main_iteration_kernel(t)
+            if mp:
+                v1, v2 = drv.cal_saturation_parts()
+                acc += v1
+            else:
+                drv.sync()
+    else:
+        # streamed steps (include/mflbm.h): every step still takes its w_in from pinned host memory and has its saturation sums
+        # read back to the host, but the copy runs beside the previous step and the result is handed out one call later
+        for t in range(1, e2e_steps + 1):
+            r = drv.step_streamed(t, w_in.data_ptr())
+            if r is not None:
+                acc += r[0]
+        if e2e_steps:
+            acc += drv.stream_flush()[0]
     ms_e2e = drv.timer_stop()
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = allreduce(max(ms_e2e, 0.0), "max")
     e2e_mlups = pore_global * e2e_steps / (ms_e2e * 1e-3) / 1e6 if e2e_steps else None
     h2d = (nx + 2) * (ny + 2) * 8
-    d2h = 2 * nz * 8 if mp else 0
+    # partial sums of cal_saturation copied back per step (kernels_monitor.cu launch_saturation: two rows of block sums)
+    red_len = 16 * max(nz, ny) + 64
+    d2h = 2 * 8 * max(1, min(148 * 8, red_len // 2, (int(pore_local) + 255) // 256)) if mp else 0
 
     # interface-rich regimes (the timed state above is a drainage front next to the inlet: most tiles are quiet)
     active = None
@@ -458,7 +472,9 @@ def main():
             "roofline_active": active,
             "e2e": None if args.no_e2e else {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / max(e2e_steps, 1), "host_wall_ms_per_step": wall_e2e / max(e2e_steps, 1),
-                    "what": "per step: mflbm_upload(w_in, pinned host) + mflbm_step + mflbm_cal_saturation read-back"},
+                    "what": ("per step: mflbm_upload(w_in, pinned host) + mflbm_step + mflbm_cal_saturation read-back (blocking calls)" if args.e2e_blocking
+                             else "per step: mflbm_step_streamed(w_in from pinned host memory, copied beside the previous step; saturation "
+                                  "sums of every step read back to the host, handed out one call later)")},
             "gpu_launches": int(main_r["launches"]), "clocks": main_r["clocks"], "parity_ngpu": parity}
     drv.close()
     if rank == 0:

@@ -164,6 +164,25 @@ module mflbm_c
             type(c_ptr), value :: ctx
             real(c_double), intent(out) :: v1, v2
         end function
+        ! streamed step: host inlet profile in, saturation sums of the PREVIOUS streamed step out (include/mflbm.h)
+        integer(c_int) function mflbm_step_streamed(ctx, ntime, w_in_host, v1, v2, have_prev) bind(c, name="mflbm_step_streamed")
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: ntime
+            type(c_ptr), value :: w_in_host   ! c_loc(w_in) of a pinned array, or c_null_ptr
+            real(c_double), intent(out) :: v1, v2
+            integer(c_int), intent(out) :: have_prev
+        end function
+        integer(c_int) function mflbm_stream_flush(ctx, v1, v2) bind(c, name="mflbm_stream_flush")
+            import :: c_int, c_ptr, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), intent(out) :: v1, v2
+        end function
+        integer(c_int) function mflbm_chain_info(ctx, fused, reject_mask) bind(c, name="mflbm_chain_info")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: ctx
+            integer(c_int), intent(out) :: fused, reject_mask
+        end function
         integer(c_int) function mflbm_monitor_breakthrough(ctx, cnt) bind(c, name="mflbm_monitor_breakthrough")
             import :: c_int, c_ptr, c_int32_t
             type(c_ptr), value :: ctx

@@ -116,6 +116,17 @@ int mflbm_download(mflbm_ctx *ctx, const mflbm_arrays *host);
 int mflbm_step(mflbm_ctx *ctx, int ntime);
 /* nsteps consecutive calls of mflbm_step starting at ntime0 (benchmark loop, MP/Main_multiphase.F90:515-531) */
 int mflbm_run(mflbm_ctx *ctx, int ntime0, int nsteps);
+/* Streamed steps: main_iteration_kernel for a driver that hands over a HOST input and wants a result back every time step
+ * (a time-dependent inlet profile, MP/Init_multiphase.F90 inlet_vel_profile_rectangular; cal_saturation as a per-step
+ * monitor, MP/Monitor.F90:472-507) without stalling the device twice per step the way mflbm_upload + mflbm_step +
+ * mflbm_cal_saturation do.  w_in_host (pinned, the reference's w_in(0:nx+1,0:ny+1); NULL = keep the current profile) is
+ * copied on the copy stream while the previous step still runs; the saturation sums of step ntime are read back
+ * asynchronously and handed out by the NEXT call: *v1, *v2 = sums after the previous streamed step, *have_prev = 0 on the
+ * first call (singlephase: no result, *have_prev stays 0; the call then only paces the host one step behind the device).
+ * mflbm_stream_flush waits for the last streamed step and returns its sums.  Results and populations are those of
+ * mflbm_step / mflbm_cal_saturation. */
+int mflbm_step_streamed(mflbm_ctx *ctx, int ntime, const double *w_in_host, double *v1, double *v2, int *have_prev);
+int mflbm_stream_flush(mflbm_ctx *ctx, double *v1, double *v2);
 /* call color_gradient (MP/Main_multiphase.F90:120 ; MP/Phase_gradient.F90:5-204) */
 int mflbm_color_gradient(mflbm_ctx *ctx);
 /* call compute_macro_vars (MP/Misc.F90:372-430 ; SP/Misc.F90:368-423) */

@@ -49,7 +49,7 @@ EXPORTS = ("mflbm_create", "mflbm_destroy", "mflbm_last_error", "mflbm_version",
            "mflbm_cal_saturation", "mflbm_monitor_breakthrough", "mflbm_monitor_steady_phasefield",
            "mflbm_monitor_steady_capillarypressure", "mflbm_set_parameter", "mflbm_sync", "mflbm_timer_start",
            "mflbm_timer_stop", "mflbm_profile", "mflbm_profile_read", "mflbm_launch_count", "mflbm_device_bytes", "mflbm_nccl_unique_id",
-           "mflbm_tile_stats", "mflbm_chain_info", "mflbm_chain_selfcheck", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
+           "mflbm_tile_stats", "mflbm_chain_info", "mflbm_chain_selfcheck", "mflbm_step_streamed", "mflbm_stream_flush", "mflbm_geometry_preprocess", "mflbm_geometry_free", "mflbm_geometry_last_error",
            "mflbm_output_begin", "mflbm_output_end", "mflbm_checkpoint_begin", "mflbm_checkpoint_fetch", "mflbm_checkpoint_end")
 
 
@@ -112,6 +112,8 @@ def load(strict=False):
     lib.mflbm_tile_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.mflbm_chain_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mflbm_chain_selfcheck.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.mflbm_step_streamed.argtypes = [vp, C.c_int, C.c_void_p, _DP, _DP, C.POINTER(C.c_int)]
+    lib.mflbm_stream_flush.argtypes = [vp, _DP, _DP]
     lib.mflbm_launch_count.argtypes = [vp]
     lib.mflbm_launch_count.restype = C.c_longlong
     lib.mflbm_device_bytes.argtypes = [vp]
@@ -286,6 +288,17 @@ class Context:
 
     def run(self, ntime0, nsteps):
         self._chk(self.lib.mflbm_run(self.h, ntime0, nsteps), "mflbm_run")
+
+    def step_streamed(self, ntime, w_in_ptr=None):
+        """one streamed step; returns (v1, v2) of the PREVIOUS streamed step or None (first call / singlephase)"""
+        v1, v2, have = C.c_double(), C.c_double(), C.c_int()
+        self._chk(self.lib.mflbm_step_streamed(self.h, ntime, w_in_ptr, C.byref(v1), C.byref(v2), C.byref(have)), "mflbm_step_streamed")
+        return (v1.value, v2.value) if have.value else None
+
+    def stream_flush(self):
+        v1, v2 = C.c_double(), C.c_double()
+        self._chk(self.lib.mflbm_stream_flush(self.h, C.byref(v1), C.byref(v2)), "mflbm_stream_flush")
+        return v1.value, v2.value
 
     def color_gradient(self):
         self._chk(self.lib.mflbm_color_gradient(self.h), "mflbm_color_gradient")

@@ -16,14 +16,15 @@ __device__ __forceinline__ double w_equ(int n) { return n <= 6 ? 1.0 / 18.0 : 1.
 // ---------------------------------------------------------------------------------------------------
 
 // K3: phi on solid boundary nodes = weighted mean over listed fluid neighbours (MP/Phase_gradient.F90:16-29)
-__device__ __forceinline__ void phi_solid_at(const Dev &P, int n) {
-    const int c = P.solid_cell[n];
-    const unsigned m = P.solid_mask[n];
+// flat = true: entry n of the flat-order copies of the lists (Dev::solid_cell_r ...)
+__device__ __forceinline__ void phi_solid_at(const Dev &P, int n, bool flat = false) {
+    const int c = (flat ? P.solid_cell_r : P.solid_cell)[n];
+    const unsigned m = (flat ? P.solid_mask_r : P.solid_mask)[n];
     double acc = 0.0;
 #pragma unroll
     for (int q = 1; q <= 18; q++)
         if (m & (1u << q)) acc = acc + P.phi[c + P.g.off(q)] * w_equ(q);
-    P.phi[c] = acc / P.solid_law[n];
+    P.phi[c] = acc / (flat ? P.solid_law_r : P.solid_law)[n];
 }
 
 // K4: ISO4 gradient of phi, norm, normalise; zero below 1e-6 (MP/Phase_gradient.F90:36-78).
@@ -51,13 +52,9 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
 }
 
 // K5: geometric wetting (Akai et al. 2018), MP/Phase_gradient.F90:225-261; cos/sin(theta) precomputed on the host
-__device__ __forceinline__ void alter_at(const Dev &P, int n) {
-    const int c = P.fluid_cell[n];
-    const size_t nf = (size_t)P.num_fluid;
-    if (!(P.c_norm[c] > 1e-6)) return;
-    const double nwx = P.fluid_nw[n], nwy = P.fluid_nw[nf + n], nwz = P.fluid_nw[2 * nf + n];
-    const double tcos = P.fluid_nw[3 * nf + n], tsin = P.fluid_nw[4 * nf + n];
-    const double x0 = P.cn_x[c], y0 = P.cn_y[c], z0 = P.cn_z[c];
+// the altered normal of one node: (x0, y0, z0) in, the closer of the two candidate directions out
+__device__ __forceinline__ void alter_normal(const double nwx, const double nwy, const double nwz, const double tcos, const double tsin,
+                                             double &x0, double &y0, double &z0) {
     const double t1 = nwx * x0 + nwy * y0 + nwz * z0;
     const double t2 = 1.0 / sqrt(1 - t1 * t1);
     const double coe1 = tsin * t1 * t2;
@@ -70,18 +67,54 @@ __device__ __forceinline__ void alter_at(const Dev &P, int n) {
     const double zm = (tcos + coe1) * nwz - coe2 * z0;
     const double dP = (xp - x0) * (xp - x0) + (yp - y0) * (yp - y0) + (zp - z0) * (zp - z0);
     const double dM = (xm - x0) * (xm - x0) + (ym - y0) * (ym - y0) + (zm - z0) * (zm - z0);
-    if (dP <= dM) {
-        P.cn_x[c] = xp; P.cn_y[c] = yp; P.cn_z[c] = zp;
+    if (dP <= dM) { x0 = xp; y0 = yp; z0 = zp; }
+    else { x0 = xm; y0 = ym; z0 = zm; }
+}
+
+// K4 + K5 in one pass over a cell list (kf = entry of the cell in the fluid boundary list of the same order -- flat or grouped
+// by tile -- or -1): the
+// normal goes from the registers of K4 straight into K5 instead of through four dense arrays (K5 alone moved 3.2 GB on C3)
+__device__ __forceinline__ void gradient_alter_at(const Dev &P, int c, int kf, bool flat) {
+    const int sx = P.g.sx, sxy = P.g.sxy;
+    const double *__restrict__ ph = P.phi;
+    double nwx = 0.0, nwy = 0.0, nwz = 0.0, tcos = 0.0, tsin = 0.0;
+    if (kf >= 0) {  // issued together with the stencil loads
+        const size_t nf = (size_t)P.num_fluid;
+        const double *__restrict__ nw = flat ? P.fluid_nw_r : P.fluid_nw;
+        nwx = nw[kf]; nwy = nw[nf + kf]; nwz = nw[2 * nf + kf]; tcos = nw[3 * nf + kf]; tsin = nw[4 * nf + kf];
+    }
+    auto v = [&](int a, int b, int d) { return ph[c + a + sx * b + sxy * d]; };
+    const double gx = ddx(v), gy = ddy(v), gz = ddz(v);
+    const double s2 = gx * gx + gy * gy + gz * gz;
+    const double cn = s2 < 0.99e-12 ? 0.0 : sqrt(s2);  // see gradient_at
+    if (cn < 1e-6) {
+        if (P.c_norm[c] == 0.0) return;
+        P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
     } else {
-        P.cn_x[c] = xm; P.cn_y[c] = ym; P.cn_z[c] = zm;
+        double x0 = gx / cn, y0 = gy / cn, z0 = gz / cn;
+        if (kf >= 0 && cn > 1e-6) alter_normal(nwx, nwy, nwz, tcos, tsin, x0, y0, z0);
+        P.cn_x[c] = x0; P.cn_y[c] = y0; P.cn_z[c] = z0; P.c_norm[c] = cn;
     }
 }
 
+__device__ __forceinline__ void alter_at(const Dev &P, int n, bool flat = false) {
+    const int c = (flat ? P.fluid_cell_r : P.fluid_cell)[n];
+    const size_t nf = (size_t)P.num_fluid;
+    if (!(P.c_norm[c] > 1e-6)) return;
+    const double *__restrict__ nw = flat ? P.fluid_nw_r : P.fluid_nw;
+    const double nwx = nw[n], nwy = nw[nf + n], nwz = nw[2 * nf + n];
+    const double tcos = nw[3 * nf + n], tsin = nw[4 * nf + n];
+    const double x0 = P.cn_x[c], y0 = P.cn_y[c], z0 = P.cn_z[c];
+    double x1 = x0, y1 = y0, z1 = z0;
+    alter_normal(nwx, nwy, nwz, tcos, tsin, x1, y1, z1);
+    P.cn_x[c] = x1; P.cn_y[c] = y1; P.cn_z[c] = z1;
+}
+
 // K6: normal on solid boundary nodes inside the 0..n+1 box (MP/Phase_gradient.F90:88-109)
-__device__ __forceinline__ void cn_solid_at(const Dev &P, int n, bool lazy = true) {
-    const unsigned m = P.solid_mask[n];
+__device__ __forceinline__ void cn_solid_at(const Dev &P, int n, bool lazy = true, bool flat = false) {
+    const unsigned m = (flat ? P.solid_mask_r : P.solid_mask)[n];
     if (!(m & 0x80000000u)) return;
-    const int c = P.solid_cell[n];
+    const int c = (flat ? P.solid_cell_r : P.solid_cell)[n];
     if (P.sparse && lazy) {
         // lazy path: if no listed fluid neighbour carries an interface (c_norm == 0 => n == 0) the result is exactly 0
         bool any = false;
@@ -104,7 +137,7 @@ __device__ __forceinline__ void cn_solid_at(const Dev &P, int n, bool lazy = tru
             ay = ay + P.cn_y[cq] * w_equ(q);
             az = az + P.cn_z[cq] * w_equ(q);
         }
-    const double law = P.solid_law[n];
+    const double law = (flat ? P.solid_law_r : P.solid_law)[n];
     P.cn_x[c] = ax / law;
     P.cn_y[c] = ay / law;
     P.cn_z[c] = az / law;
@@ -401,6 +434,7 @@ __global__ void k_tile_all(const Dev P) {
 template <int K>
 __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp, int force) {
     if (!force && !P.tcount[3]) return;  // most tiles active: k_chain_flat<K> runs instead (or nothing is left to do)
+    if (K == 5 && P.gk5) return;         // done by K4
     const int *__restrict__ list = K == 3 ? P.tk3 : P.tact;
     const int count = P.tcount[K == 3 ? 1 : 0];
     const int *__restrict__ start = (K == 3 || K == 6) ? P.ts_start : (K == 4 ? P.tg_start : P.tf_start);
@@ -410,8 +444,10 @@ __global__ void __launch_bounds__(64) k_chain_tiles(const Dev P, int stamp, int 
         const int e1 = start[tile + 1];
         for (int e = start[tile] + threadIdx.x; e < e1; e += 64) {
             if (K == 3) phi_solid_at(P, e);
-            else if (K == 4) gradient_at<true>(P, P.gcell[e]);
-            else if (K == 5) alter_at(P, e);
+            else if (K == 4) {
+                if (P.gk5) gradient_alter_at(P, P.gcell[e], P.gk5[e], false);
+                else gradient_at<true>(P, P.gcell[e]);
+            } else if (K == 5) alter_at(P, e);
             else cn_solid_at(P, e);
         }
     }
@@ -441,12 +477,33 @@ __global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
     const int count = (K == 3 || K == 6) ? P.num_solid : (K == 4 ? P.nG : P.num_fluid);
     // K6: the 18 extra |grad phi| reads of the lazy path only pay while a good part of the lattice has no interface
     const bool lazy = (long long)P.tcount[0] * 2 < (long long)P.ntiles;
+    if (K == 5 && P.gk5_r) return;  // done by the K4 sweep
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
-        if (K == 3) phi_solid_at(P, e);
-        else if (K == 4) gradient_at<true>(P, P.gcell_r[e]);
-        else if (K == 5) alter_at(P, e);
-        else cn_solid_at(P, e, lazy);
+        if (K == 3) phi_solid_at(P, e, true);
+        else if (K == 4) {
+            if (P.gk5_r) gradient_alter_at(P, P.gcell_r[e], P.gk5_r[e], true);
+            else gradient_at<true>(P, P.gcell_r[e]);
+        } else if (K == 5) alter_at(P, e, true);
+        else cn_solid_at(P, e, lazy, true);
     }
+}
+
+// Dev::gk5_r: scatter the flat-order fluid-list entries over a dense map (-1 = none), then read it back per K4 cell
+__global__ void k_gk5_scatter(const int *__restrict__ fluid_cell, int num_fluid, int *map, int *dup) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= num_fluid) return;
+    if (atomicExch(&map[fluid_cell[n]], n) != -1) atomicAdd(dup, 1);
+}
+__global__ void k_gk5_gather(const int *__restrict__ gcell, int nG, const int *map, int *gk5) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nG) gk5[e] = map[gcell[e]];
+}
+// flat = true: gk5_r from (gcell_r, fluid_cell_r); false: gk5 from the lists grouped by tile
+void launch_build_gk5(mflbm_ctx *c, cudaStream_t st, int *map, int *dup, bool flat) {
+    const Dev &P = c->d;
+    if (P.num_fluid > 0) k_gk5_scatter<<<(P.num_fluid + 255) / 256, 256, 0, st>>>(flat ? P.fluid_cell_r : P.fluid_cell, P.num_fluid, map, dup);
+    k_gk5_gather<<<(P.nG + 255) / 256, 256, 0, st>>>(flat ? P.gcell_r : P.gcell, P.nG, map, flat ? P.gk5_r : P.gk5);
+    c->launches += 2;
 }
 
 // K7 + packing (Dev::G): one thread per fluid node of every ACTIVE warp (32 consecutive A nodes).  The blocks scan the
@@ -519,8 +576,9 @@ __global__ void __launch_bounds__(256, MFLBM_PACK_MINB) k_gradient_pack_all(cons
         const int chunk = s_chunk;
         __syncthreads();
         if (chunk >= nchunk) return;
-        const int n = (chunk << 8) + threadIdx.x;
-        if (n >= P.nA) continue;
+        const int e = (chunk << 8) + threadIdx.x;
+        if (e >= P.nA) continue;
+        const int n = P.aorder ? P.aorder[e] : e;  // flat order (bricks): the chunk's stencils overlap in y and z as well
         const int c = P.cellA[n];
         const double cnorm = P.c_norm[c];
         double cnx = 0.0, cny = 0.0, cnz = 0.0, tmp = 0.0;

@@ -151,10 +151,26 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->pdf_alloc = false;
     ctx->tiles_static_ready = false;
     ctx->solid_phi_stale = false;
-    // fused colour-gradient chain (kernels_march.cu) on the sparse multiphase layout; MFLBM_MARCH=0 keeps the list kernels
-    ctx->march_on = !(getenv("MFLBM_MARCH") && atoi(getenv("MFLBM_MARCH")) == 0);
+    // fused colour-gradient chain (kernels_march.cu) on the sparse multiphase layout.  MEASURED (r02_march1 / march2, B200, C3
+    // with random phi): bit-exact, DRAM traffic 4.6 GB per evaluation against 15 GB for the five list kernels, and still
+    // slower -- 7.3 ms against 5.1 ms: 3.3 G warp instructions at 1.6 per cycle with the 16 warps per SM its 180 KB of
+    // shared memory leave room for (stalls: fixed-latency dependencies and the two barriers per plane, no memory stall at
+    // all).  The chain is bound by instruction latency, not by bytes.  Opt-in: MFLBM_MARCH=1.
+    ctx->march_on = getenv("MFLBM_MARCH") && atoi(getenv("MFLBM_MARCH")) != 0;
     ctx->march_ready = false;
     ctx->march_reject = 0;
+    for (int b = 0; b < 2; b++) {
+        ctx->win_dev[b] = ctx->win_stage[b] = ctx->res_dev[b] = ctx->res_host[b] = nullptr;
+        ctx->ev_win[b] = ctx->ev_res[b] = ctx->ev_step[b] = nullptr;
+        ctx->res_np[b] = 0;
+    }
+    ctx->stream_count = 0;
+    // order of the flat sweeps of the gradient chain (Dev::gcell_r): bricks of bx x by x bz cells; bx = 0: as wide as the lattice
+    ctx->flat_bx = 0; ctx->flat_by = 1; ctx->flat_bz = 1;
+    if (const char *b = getenv("MFLBM_BRICK")) {
+        int x = 0, y = 1, z = 1;
+        if (sscanf(b, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1 && z >= 1) { ctx->flat_bx = x; ctx->flat_by = y; ctx->flat_bz = z; }
+    }
     ctx->march_lz_flat = getenv("MFLBM_MARCH_LZ") ? std::max(1, atoi(getenv("MFLBM_MARCH_LZ"))) : 64;
     ctx->cn_dense_valid = true;
     ctx->tile_stamp = 0;
@@ -312,6 +328,12 @@ extern "C" void mflbm_destroy(mflbm_ctx *ctx) {
         if (ctx->halo_buf[b]) cudaFree(ctx->halo_buf[b]);
     if (ctx->red_dev) cudaFree(ctx->red_dev);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->res_host[b]) cudaFreeHost(ctx->res_host[b]);
+        if (ctx->ev_win[b]) cudaEventDestroy(ctx->ev_win[b]);
+        if (ctx->ev_res[b]) cudaEventDestroy(ctx->ev_res[b]);
+        if (ctx->ev_step[b]) cudaEventDestroy(ctx->ev_step[b]);
+    }
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
@@ -353,6 +375,22 @@ static void sort_by_tile(const std::vector<int> &tile, int ntiles, std::vector<i
     std::vector<int> pos(start.begin(), start.end() - 1);
     order.resize(tile.size());
     for (size_t n = 0; n < tile.size(); n++) order[(size_t)pos[tile[n]]++] = (int)n;
+}
+
+// Order of the flat sweeps (Dev::gcell_r): stable counting sort of a list of cells by brick, so that a list that comes in
+// raster order keeps it inside every brick.  order[r] = position in the input of the r-th entry in flat order.
+static void flat_order(const mflbm_ctx *ctx, const int *cells, size_t n, std::vector<int> &order) {
+    const Grid &g = ctx->d.g;
+    const int bx = ctx->flat_bx, by = ctx->flat_by, bz = ctx->flat_bz;
+    const int nbx = bx > 0 ? (g.sx + bx - 1) / bx : 1, nby = (g.ny + 8 + by - 1) / by, nbz = (g.nz + 8 + bz - 1) / bz;
+    std::vector<int> brick(n), start;
+#pragma omp parallel for schedule(static)
+    for (long long e = 0; e < (long long)n; e++) {
+        unsigned ix, jy, kz;
+        g.coords3(cells[e], ix, jy, kz);
+        brick[(size_t)e] = (bx > 0 ? (int)ix / bx : 0) + nbx * ((int)jy / by + nby * ((int)kz / bz));
+    }
+    sort_by_tile(brick, nbx * nby * nbz, order, start);
 }
 
 // Host-only part (integer work, OpenMP): node numbering and the compressed adjacency of the odd step.
@@ -620,9 +658,22 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
                 if (W(i, j, k) != 1) gcell[n++] = g.cell(i, j, k);
     }
     d.nG = (int)nG;
-    if (d.use_tiles && nG > 0) {  // flat sweeps (most tiles active) keep the raster order
+    if (d.use_tiles && nG > 0) {  // flat sweeps (most tiles active): brick order (plain raster order by default)
         if (dev_alloc(ctx, &d.gcell_r, gcell.size(), false)) return MFLBM_ERR_CUDA;
-        CU(cudaMemcpy(d.gcell_r, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (ctx->flat_bx == 0 && ctx->flat_by == 1 && ctx->flat_bz == 1) {
+            CU(cudaMemcpy(d.gcell_r, gcell.data(), gcell.size() * sizeof(int), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<int> order, sorted((size_t)nG);
+            flat_order(ctx, gcell.data(), (size_t)nG, order);
+#pragma omp parallel for schedule(static)
+            for (long long n = 0; n < nG; n++) sorted[(size_t)n] = gcell[(size_t)order[(size_t)n]];
+            CU(cudaMemcpy(d.gcell_r, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (nA > 0) {  // K7 + packing walk the fluid nodes in the same order
+                flat_order(ctx, cellA.data(), (size_t)nA, order);
+                if (dev_alloc(ctx, &d.aorder, (size_t)nA, false)) return MFLBM_ERR_CUDA;
+                CU(cudaMemcpy(d.aorder, order.data(), (size_t)nA * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
     }
     if (d.use_tiles && nG > 0) {  // tile-driven gradient chain: gcell grouped by tile (raster order inside a tile)
         std::vector<int> tile((size_t)nG), order, start;
@@ -797,6 +848,23 @@ static int xfer_pdf(mflbm_ctx *ctx, double *dev, double *host, bool up, int q, c
     return 0;
 }
 
+// Dev::gk5_r from the flat-order fluid list: returns the number of cells listed more than once, -1 on a CUDA error
+static int build_gk5(mflbm_ctx *ctx, bool flat) {
+    Dev &d = ctx->d;
+    int *map = nullptr, *dup = nullptr;
+    if (cudaMalloc((void **)&map, (size_t)d.g.ntot * sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMalloc((void **)&dup, sizeof(int)) != cudaSuccess) { cudaFree(map); return -1; }
+    cudaMemsetAsync(map, 0xff, (size_t)d.g.ntot * sizeof(int), ctx->s_main);
+    cudaMemsetAsync(dup, 0, sizeof(int), ctx->s_main);
+    launch_build_gk5(ctx, ctx->s_main, map, dup, flat);
+    int h = -1;
+    const bool ok = cudaMemcpyAsync(&h, dup, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_main) == cudaSuccess &&
+                    cudaStreamSynchronize(ctx->s_main) == cudaSuccess;
+    cudaFree(map);
+    cudaFree(dup);
+    return ok ? h : -1;
+}
+
 extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
     if (!ctx || !h) return fail(ctx, MFLBM_ERR_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
@@ -811,6 +879,8 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
         // cells outside the (-1:n+2) box keep walls=0 like an untouched allocation would; they are never read
         launch_repack_i8(ctx, ctx->s_main, d.walls, (int8_t *)ctx->stage, 2, true);
         CU(cudaStreamSynchronize(ctx->s_main));
+        d.gk5 = nullptr;
+        d.gk5_r = nullptr;  // belongs to the cell list of the previous wall array; rebuilt with the next fluid boundary list
         if (setup_populations(ctx, h->walls)) return MFLBM_ERR_CUDA;
     }
     for (int q = 0; q < 19; q++) {
@@ -854,6 +924,24 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             mask[n] = m;
             law[n] = s.la_weight;
         }
+        if (d.tcls[0]) {  // the flat sweeps read the list in flat order (Dev::gcell_r)
+            std::vector<int> order;
+            flat_order(ctx, cell.data(), cell.size(), order);
+            std::vector<int> cell2(d.num_solid);
+            std::vector<unsigned> mask2(d.num_solid);
+            std::vector<double> law2(d.num_solid);
+            for (int n = 0; n < d.num_solid; n++) {
+                cell2[n] = cell[order[n]]; mask2[n] = mask[order[n]]; law2[n] = law[order[n]];
+            }
+            if (!d.solid_cell_r && (dev_alloc(ctx, &d.solid_cell_r, d.num_solid, false) || dev_alloc(ctx, &d.solid_mask_r, d.num_solid, false) ||
+                                    dev_alloc(ctx, &d.solid_law_r, d.num_solid, false)))
+                return MFLBM_ERR_CUDA;
+            CU(cudaMemcpy(d.solid_cell_r, cell2.data(), cell2.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.solid_mask_r, mask2.data(), mask2.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.solid_law_r, law2.data(), law2.size() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            d.solid_cell_r = d.solid_cell; d.solid_mask_r = d.solid_mask; d.solid_law_r = d.solid_law;
+        }
         if (d.tcls[0]) {  // group by tile for the tile-driven chain (entries are independent of each other)
             std::vector<int> tile(d.num_solid), order, start;
             for (int n = 0; n < d.num_solid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
@@ -885,6 +973,30 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
             nw[4 * nf + n] = sin(s.theta);
         }
         if (d.tcls[0]) {
+            std::vector<int> order;
+            flat_order(ctx, cell.data(), cell.size(), order);
+            std::vector<int> cell2(d.num_fluid);
+            std::vector<double> nw2((size_t)5 * d.num_fluid);
+            for (int n = 0; n < d.num_fluid; n++) {
+                cell2[n] = cell[order[n]];
+                for (int m = 0; m < 5; m++) nw2[(size_t)m * d.num_fluid + n] = nw[(size_t)m * d.num_fluid + order[n]];
+            }
+            if (!d.fluid_cell_r && (dev_alloc(ctx, &d.fluid_cell_r, d.num_fluid, false) || dev_alloc(ctx, &d.fluid_nw_r, (size_t)5 * d.num_fluid, false)))
+                return MFLBM_ERR_CUDA;
+            CU(cudaMemcpy(d.fluid_cell_r, cell2.data(), cell2.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d.fluid_nw_r, nw2.data(), nw2.size() * sizeof(double), cudaMemcpyHostToDevice));
+            // K4 + K5 in one flat sweep: which entry of this list belongs to each K4 cell (none: -1).  A cell listed twice
+            // would have K5 applied twice by the separate sweep, so the fusion is only taken for lists without repeats.
+            if (d.nG > 0 && d.gcell_r && !getenv("MFLBM_NO_K45")) {
+                if (!d.gk5_r && dev_alloc(ctx, &d.gk5_r, (size_t)d.nG, false)) return MFLBM_ERR_CUDA;
+                const int dup = build_gk5(ctx, true);
+                if (dup < 0) return MFLBM_ERR_CUDA;
+                if (dup > 0) d.gk5_r = nullptr;  // (the allocation stays on ctx->allocs)
+            }
+        } else {
+            d.fluid_cell_r = d.fluid_cell; d.fluid_nw_r = d.fluid_nw;
+        }
+        if (d.tcls[0]) {
             std::vector<int> tile(d.num_fluid), order, start;
             for (int n = 0; n < d.num_fluid; n++) tile[n] = g.tile_of(cell[n], d.ntx, d.nty);
             sort_by_tile(tile, d.ntiles, order, start);
@@ -899,6 +1011,10 @@ extern "C" int mflbm_upload(mflbm_ctx *ctx, const mflbm_arrays *h) {
         }
         CU(cudaMemcpy(d.fluid_cell, cell.data(), cell.size() * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.fluid_nw, nw.data(), nw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (d.tcls[0] && d.gk5_r && d.gcell && !d.k4_smem) {  // the same fusion for the tile-driven K4 (lists grouped by tile)
+            if (!d.gk5 && dev_alloc(ctx, &d.gk5, (size_t)d.nG, false)) return MFLBM_ERR_CUDA;
+            if (build_gk5(ctx, false) != 0) d.gk5 = nullptr;
+        }
     }
     return MFLBM_OK;
 }
@@ -1201,6 +1317,102 @@ extern "C" int mflbm_run(mflbm_ctx *ctx, int ntime0, int nsteps) {
         const int rc = step_impl(ctx, ntime0 + n);
         if (rc) return rc;
     }
+    return MFLBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// streamed steps (include/mflbm.h "streamed steps"): per-step host input and per-step result without a host stall
+// ---------------------------------------------------------------------------------------------------
+static int stream_setup(mflbm_ctx *ctx) {
+    if (ctx->win_stage[0]) return 0;
+    Dev &d = ctx->d;
+    const size_t nplane = (size_t)d.g.sxy + 32, npack = (size_t)(d.g.nx + 2) * (d.g.ny + 2);
+    ctx->win_dev[0] = d.w_in;
+    if (dev_alloc(ctx, &ctx->win_dev[1], nplane)) return MFLBM_ERR_CUDA;
+    for (int b = 0; b < 2; b++) {
+        if (dev_alloc(ctx, &ctx->win_stage[b], npack, false) || dev_alloc(ctx, &ctx->res_dev[b], (size_t)ctx->red_len)) return MFLBM_ERR_CUDA;
+        CU(cudaMallocHost((void **)&ctx->res_host[b], ctx->red_len * sizeof(double)));
+        CU(cudaEventCreateWithFlags(&ctx->ev_win[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_res[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_step[b], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// result slot b -> sums (waits for its read-back only)
+static int stream_result(mflbm_ctx *ctx, int b, double *v1, double *v2) {
+    CU(cudaEventSynchronize(ctx->ev_res[b]));
+    double a = 0, c = 0;
+    const int np = ctx->res_np[b];
+    for (int k = 0; k < np; k++) { a += ctx->res_host[b][k]; c += ctx->res_host[b][np + k]; }
+    if (v1) *v1 = a;
+    if (v2) *v2 = c;
+    return 0;
+}
+
+extern "C" int mflbm_step_streamed(mflbm_ctx *ctx, int ntime, const double *w_in_host, double *v1, double *v2, int *have_prev) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->pdf_alloc) return fail(ctx, MFLBM_ERR_STATE, "mflbm_step_streamed before mflbm_upload");
+    if (stream_setup(ctx)) return MFLBM_ERR_CUDA;
+    Dev &d = ctx->d;
+    const int b = (int)(ctx->stream_count & 1), prev = b ^ 1;
+    if (w_in_host) {
+        // this step's inlet profile: host -> staging -> padded plane, on the copy stream, beside the previous step; the
+        // buffers of slot b were last read by the streamed step before the previous one
+        if (ctx->stream_count >= 2) {
+            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_step[b], 0));
+        } else {  // ... or by whatever ran before the first streamed step
+            CU(cudaEventRecord(ctx->ev_win[b], ctx->s_main));
+            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_win[b], 0));
+        }
+        const size_t npack = (size_t)(d.g.nx + 2) * (d.g.ny + 2);
+        CU(cudaMemcpyAsync(ctx->win_stage[b], w_in_host, npack * sizeof(double), cudaMemcpyHostToDevice, ctx->s_copy));
+        launch_repack(ctx, ctx->s_copy, ctx->win_dev[b], ctx->win_stage[b], 1, 1, -3, true);
+        CU(cudaEventRecord(ctx->ev_win[b], ctx->s_copy));
+        CU(cudaStreamWaitEvent(ctx->s_main, ctx->ev_win[b], 0));
+        d.w_in = ctx->win_dev[b];
+    }
+    // the saturation kernel of the previous streamed step reads phi beside that step's gradient chain: the collision of
+    // this step must not overwrite it
+    if (ctx->stream_count >= 1 && d.multiphase) CU(cudaStreamWaitEvent(ctx->s_main, ctx->ev_res[prev], 0));
+    const int rc = step_impl(ctx, ntime);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_step[b], ctx->s_main));
+    if (d.multiphase) {  // cal_saturation of this step, read back asynchronously (like mflbm_cal_saturation: after ev_phi, second stream)
+        cudaStream_t st = ctx->s_main;
+        if (d.sparse && ctx->ev_phi_valid) {
+            st = ctx->s_halo;
+            CU(cudaStreamWaitEvent(st, ctx->ev_phi, 0));
+        }
+        ctx->res_np[b] = launch_saturation(ctx, st, ctx->res_dev[b]);
+        CU(cudaMemcpyAsync(ctx->res_host[b], ctx->res_dev[b], 2 * ctx->res_np[b] * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->ev_res[b], st));
+    }
+    if (have_prev) *have_prev = 0;
+    if (ctx->stream_count >= 1) {  // pace the host one step behind the device and hand out the previous step's result
+        if (d.multiphase) {
+            if (stream_result(ctx, prev, v1, v2)) return MFLBM_ERR_CUDA;
+            if (have_prev) *have_prev = 1;
+        } else {
+            CU(cudaEventSynchronize(ctx->ev_step[prev]));
+        }
+    }
+    ctx->stream_count++;
+    return check_launch(ctx);
+}
+
+extern "C" int mflbm_stream_flush(mflbm_ctx *ctx, double *v1, double *v2) {
+    if (!ctx) return fail(nullptr, MFLBM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->stream_count < 1) return fail(ctx, MFLBM_ERR_STATE, "no streamed step in flight");
+    const int last = (int)((ctx->stream_count - 1) & 1);
+    if (ctx->d.multiphase) {
+        if (stream_result(ctx, last, v1, v2)) return MFLBM_ERR_CUDA;
+        CU(cudaStreamWaitEvent(ctx->s_main, ctx->ev_res[last], 0));  // whatever the caller queues next comes after the read-back
+    }
+    CU(cudaStreamSynchronize(ctx->s_main));
+    ctx->stream_count = 0;
     return MFLBM_OK;
 }
 

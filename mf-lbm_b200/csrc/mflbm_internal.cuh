@@ -128,8 +128,18 @@ struct Dev {
     int *smap;        // [ntot] dense cell -> active index, -1 if not active
     int *gcell;       // [nG] non-solid cells of the (-1:n+2)^3 box: where the colour gradient is evaluated (grouped by tile
                       // when use_tiles, raster order otherwise)
-    int *gcell_r;     // the same cells in raster order (k, j, i): the flat K4 sweep reads whole rows with it (use_tiles only)
+    int *gcell_r;     // the same cells in the order of the FLAT sweeps (use_tiles only): bricks of flat_bx x flat_by x flat_bz
+                      // cells, raster order (k, j, i) inside a brick and from brick to brick; one brick as wide as the lattice
+                      // and one row high = plain raster order.  Consecutive threads then work on x-runs of neighbouring rows
+                      // and planes, so the 18-neighbour stencils of a block share their operands in L1.
+    int *gk5_r;       // [nG] parallel to gcell_r: index of the cell in the flat-order fluid boundary list, -1 if it has no
+                      // entry: the flat K4 sweep then applies K5 (geometric wetting) on the spot and the K5 sweep is skipped
+    int *gk5;         // the same for gcell and the fluid boundary list grouped by tile (tile-driven K4)
     int nG;
+    // the node lists and the active nodes in flat order (see gcell_r), for the flat sweeps of K3 / K6 / K7
+    int *solid_cell_r, *fluid_cell_r, *aorder;  // aorder[e] = active index of the e-th fluid node in flat order
+    unsigned *solid_mask_r;
+    double *solid_law_r, *fluid_nw_r;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
     // sparse multiphase layout: what the collision kernel needs of the colour gradient, PACKED by active index n so that a
     // warp reads four coalesced 256-byte rows: G[0..2] = interface normal n (after K4 + K5), G[3] = 0.5*gamma*curv*|grad phi|
@@ -295,6 +305,13 @@ struct mflbm_ctx {
     bool macro_alloc;
     bool pdf_alloc;
     // march kernel (kernels_march.cu): fused colour-gradient chain of the sparse multiphase layout
+    // streamed steps (mflbm_step_streamed): double-buffered inlet profile and result slots
+    double *win_dev[2], *win_stage[2];  // device w_in alternates (win_dev[0] is the upload's array) / packed host-layout staging
+    double *res_dev[2], *res_host[2];   // partial sums of cal_saturation, device / pinned host
+    cudaEvent_t ev_win[2], ev_res[2], ev_step[2];
+    int res_np[2];
+    long long stream_count;             // streamed steps so far
+    int flat_bx, flat_by, flat_bz;  // brick of the flat-sweep order (MFLBM_BRICK="bx,by,bz")
     bool march_on;            // selected for this context (MFLBM_MARCH=0 keeps the list kernels)
     bool march_ready;         // cell codes built for the current walls / node lists
     int march_reject;         // why the node lists were not accepted (bit mask, 0 = accepted)
@@ -325,6 +342,7 @@ void launch_tiles_reset(mflbm_ctx *c, cudaStream_t st);
 int tiles_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_curvature(mflbm_ctx *c, cudaStream_t st);
 void launch_gradient_pack(mflbm_ctx *c, cudaStream_t st);
+void launch_build_gk5(mflbm_ctx *c, cudaStream_t st, int *map, int *dup, bool flat);
 int march_prepare(mflbm_ctx *c, cudaStream_t st);
 void launch_march(mflbm_ctx *c, cudaStream_t st, int mode, int stamp);
 void launch_dense_gradient(mflbm_ctx *c, cudaStream_t st);

@@ -159,4 +159,24 @@ def live_phi_mask(o):
     hi = w[2:-2, 2:-2, 2 + nz - 1] != 0  # walls(i,j,nz)
     m[4:-4, 4:-4, 0][lo] = False
     m[4:-4, 4:-4, -1][hi] = False
+    if o.p.kper and o.p.npz == 1:
+        # z-periodic: the same two planes are images of the planes nz-3 and 4 (MP/Mpi.F90:624-631), copied BEFORE this step's
+        # K3: at solid cells they hold the previous step's K3 result of the image cell -- equally without a consumer (solid, so
+        # no K3 of plane -2 / nz+3 reads them; outside the list; outside every gradient stencil), and the fused chain kernel
+        # (csrc/march.cuh) never stores K3 results at all, so only the fluid cells of these planes are compared
+        fl_lo = np.zeros(phi.shape[:2], bool)
+        fl_hi = np.zeros(phi.shape[:2], bool)
+        fl_lo[2:-2, 2:-2] = w[:, :, 2 + (nz - 3) - 1] == 0   # walls(i,j,nz-3), i,j in -1..n+2
+        fl_hi[2:-2, 2:-2] = w[:, :, 2 + 4 - 1] == 0          # walls(i,j,4)
+        m[:, :, 0] &= fl_lo
+        m[:, :, -1] &= fl_hi
+    if o.p.jper:
+        # y-periodic: likewise the outermost ghost rows j = -3 and j = ny+4, images of the rows ny-3 and 4 (MP/Mpi.F90:633-790)
+        ny = o.ny
+        fl_lo = np.zeros((phi.shape[0], phi.shape[2]), bool)
+        fl_hi = np.zeros((phi.shape[0], phi.shape[2]), bool)
+        fl_lo[2:-2, 2:-2] = w[:, 2 + (ny - 3) - 1, :] == 0
+        fl_hi[2:-2, 2:-2] = w[:, 2 + 4 - 1, :] == 0
+        m[:, 0, :] &= fl_lo
+        m[:, -1, :] &= fl_hi
     return m

@@ -65,3 +65,37 @@ def test_staged_output_singlephase_and_errors():
         r = o.field(nme)[inner]
         assert np.max(np.abs(got[nme][inner] - r)) <= 1e-13 * max(1e-30, np.max(np.abs(r))), nme
     ctx.close()
+
+
+def test_streamed_steps_equal_blocking_steps():
+    """mflbm_step_streamed (host inlet profile copied beside the previous step, saturation sums handed out one call later) leaves
+    exactly the state of mflbm_upload(w_in) + mflbm_step, and every step's sums equal mflbm_cal_saturation after that step"""
+    import ctypes as C
+    import torch
+    o = make_oracle(modify_geometry_cmd=1, ca_0=5e-3)
+    a = ctx_from_oracle(o, strict=True, kernel_variant=2)
+    b = ctx_from_oracle(o, strict=True, kernel_variant=2)
+    a.color_gradient(); b.color_gradient()
+    w0 = np.asfortranarray(o.field("w_in")).copy(order="F")
+    pin = torch.zeros(w0.size, dtype=torch.float64).pin_memory()
+    want, got = [], []
+    for t in range(1, 14):
+        w = w0 * (1.0 + 0.01 * t)  # a time-dependent inlet profile
+        a.upload(w_in=w)
+        a.step(t)
+        want.append(a.cal_saturation())
+        if t > 1:  # the pinned buffer of step t-1 may be reused once that step's copy is done: the call for t-1 has returned
+            b.sync()
+        pin.copy_(torch.from_numpy(np.ascontiguousarray(w.ravel(order="F"))))
+        r = b.step_streamed(t, pin.data_ptr())
+        assert (r is None) == (t == 1)
+        if r is not None:
+            got.append(r)
+    got.append(b.stream_flush())
+    assert got == want
+    fa, fb = a.download("f", "g", "phi"), b.download("f", "g", "phi")
+    for n in ("f", "g"):
+        for q in range(19):
+            assert np.array_equal(fa[n][q], fb[n][q]), (n, q)
+    assert np.array_equal(fa["phi"], fb["phi"])
+    a.close(); b.close()

@@ -165,7 +165,6 @@ def test_speculative_early_chain_is_exact(force, monkeypatch):
     whether the guessed layer range is right, completely wrong (every active tile is "missed" and the chain re-runs on the
     full lists) or partly right."""
     monkeypatch.setenv("MFLBM_SPEC", "1")  # measured: no gain on B200, so the schedule is opt-in; it must still be exact
-    monkeypatch.setenv("MFLBM_MARCH", "0")  # the schedule belongs to the list kernels of the chain (the fused kernel replaces both)
     if force:
         monkeypatch.setenv("MFLBM_SPEC_FORCE", force)
     rng = np.random.default_rng(23)

@@ -44,7 +44,7 @@ __device__ __forceinline__ void gradient_at(const Dev &P, int c) {
     const double cn = s2 < 0.99e-12 ? 0.0 : sqrt(s2);
     if (cn < 1e-6) {
         // LAZY (sparse layout): bulk nodes already hold zeros; c_norm == 0 implies n == 0 at non-solid nodes
-        if (LAZY && P.c_norm[c] == 0.0) return;
+        if (LAZY && P.lazy_ok && P.c_norm[c] == 0.0) return;
         P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
     } else {
         P.cn_x[c] = gx / cn; P.cn_y[c] = gy / cn; P.cn_z[c] = gz / cn; P.c_norm[c] = cn;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void gradient_alter_at(const Dev &P, int c, int kf, b
     const double s2 = gx * gx + gy * gy + gz * gz;
     const double cn = s2 < 0.99e-12 ? 0.0 : sqrt(s2);  // see gradient_at
     if (cn < 1e-6) {
-        if (P.c_norm[c] == 0.0) return;
+        if (P.lazy_ok && P.c_norm[c] == 0.0) return;
         P.cn_x[c] = 0.0; P.cn_y[c] = 0.0; P.cn_z[c] = 0.0; P.c_norm[c] = 0.0;
     } else {
         double x0 = gx / cn, y0 = gy / cn, z0 = gz / cn;
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) k_chain_flat(const Dev P) {
     if (!P.tcount[2]) return;
     const int count = (K == 3 || K == 6) ? P.num_solid : (K == 4 ? P.nG : P.num_fluid);
     // K6: the 18 extra |grad phi| reads of the lazy path only pay while a good part of the lattice has no interface
-    const bool lazy = (long long)P.tcount[0] * 2 < (long long)P.ntiles;
+    const bool lazy = P.lazy_ok && (long long)P.tcount[0] * 2 < (long long)P.ntiles;
     if (K == 5 && P.gk5_r) return;  // done by the K4 sweep
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         if (K == 3) phi_solid_at(P, e, true);
@@ -776,6 +776,34 @@ long long chain_selfcheck(mflbm_ctx *c, cudaStream_t st) {
 void launch_color_gradient(mflbm_ctx *c, cudaStream_t st, bool stepping) {
     Dev &P = c->d;
     if (!P.multiphase) return;
+    if (c->march_on && c->march_ready && c->march_hybrid && P.use_tiles) {
+        // hybrid: the fused kernel where few tiles are active (the work items around them), the flat sweeps of the list kernels
+        // where most are -- whichever the tile update selects on the device.  The dense arrays are current only after a flat
+        // evaluation, which the host cannot know: they count as stale, and the flat sweeps run without lazy shortcuts.
+        c->solid_phi_stale = true;
+        c->cn_dense_valid = false;
+        cudaMemsetAsync(P.tcount, 0, 12 * sizeof(int), st);
+        const int nb = (P.ntiles + 127) / 128;
+        if (stepping) {
+            k_tile_update<<<nb, 128, 0, st>>>(P, P.tile_cur, ++c->tile_stamp, 0, P.ntz - 1, 1);
+            k_tile_mode<<<1, 1, 0, st>>>(P, 0);
+            c->launches += 2;
+            P.wq_stamp = c->tile_stamp;
+            P.wq_all = 0;
+            P.tile_cur ^= 1;
+        } else {
+            launch_tiles_reset(c, st);
+            k_tile_all<<<nb, 128, 0, st>>>(P);  // tcount[2] = 1: the flat sweeps run
+            c->launches++;
+        }
+        launch_chain_kernels(c, st, false, false);  // flat sweeps, gated by tcount[2]
+        static int cap_all = 0;
+        if (!cap_all) cap_all = resident_grid(k_gradient_pack_all, 256);
+        k_gradient_pack_all<<<std::min(cap_all, (P.nA + 255) / 256), 256, 0, st>>>(P, 0);
+        c->launches++;
+        if (stepping) launch_march(c, st, 2, c->tile_stamp);  // gated by tcount[3]
+        return;
+    }
     if (c->march_on && c->march_ready) {
         // one kernel (march.cuh); phi on the solid nodes and the dense normal arrays are not written
         c->solid_phi_stale = true;

@@ -52,8 +52,15 @@ __global__ void __launch_bounds__(MARCH_NT, 1) k_march(const Dev P, const int lz
         if (w >= count) return;
         const int item = mode == 2 ? P.mlist[w] : w;
         const int col = item % ncol, ch = item / ncol;
+        int ch1 = ch;
+        if (mode == 2) {
+            // listed items on top of each other in one column are marched through in one go by the lowest of them: the six
+            // ramp-up and four run-out planes are paid once per run instead of once per item
+            if (ch > 0 && P.mflag[item - ncol] == stamp) continue;
+            while (ch1 + 1 < nchunk && P.mflag[item + (ch1 + 1 - ch) * ncol] == stamp) ch1++;
+        }
         const int kA = 1 + ch * lz;
-        const int kB = min(P.g.nz, kA + lz - 1);
+        const int kB = min(P.g.nz, (ch1 + 1) * lz);
         march_block(P, S, col % P.mcols_x, col / P.mcols_x, kA, kB, mode == 2 ? stamp : 0);
     }
 }

@@ -147,6 +147,13 @@ MH_FN void m_wait1() {  // all but the most recent group have landed
 }
 
 __host__ __device__ __forceinline__ int m_slot(int q, int ring) { return (q + 10 * ring) % ring; }  // q >= -4 always
+// slot of plane t - k (k in -2..6) given r = slot of plane t: the modulo is taken once per ring and tick (r is carried along),
+// not once per use (r02 profile: the ring-index arithmetic was 11 % of the instructions)
+__host__ __device__ __forceinline__ int m_rel(int r, int k, int ring) {
+    const int kk = ((k % ring) + ring) % ring;  // constants: folded at compile time
+    const int v = r - kk;
+    return v < 0 ? v + ring : v;
+}
 
 // One block: column (bx, by), planes kA..kB (1 <= kA <= kB <= nz).  stamp > 0: stamp the warps of the nodes written (Dev::wstamp).
 MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, const int kA, const int kB,
@@ -160,18 +167,19 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
     const double gamma_half = 0.5 * P.gamma;
 
     // asynchronous loads of plane q: phi and codes (halo 4), and the active indices of plane qs (the column itself)
-    auto issue_loads = [&](const int tid, const int q, const bool want, const int qs, const bool want_s) {
+    auto issue_loads = [&](const int tid, const int q, const bool want, const int qs, const bool want_s, const int sl_phi, const int sl_code,
+                           const int sl_smap) {
         if (want) {
             const long long pbase = cell00 + (long long)sxy * (q + 3);
             if (tid < M_PY4 * (M_PX4 / 2)) {  // 480 chunks of two doubles
                 const int lj = tid / (M_PX4 / 2), li = 2 * (tid % (M_PX4 / 2));
-                double *dst = &S.phi[m_slot(q, M_RPHI)][li + M_PX4 * lj];
+                double *dst = &S.phi[sl_phi][li + M_PX4 * lj];
                 if (i0 - 1 + li < sx && j0 - 1 + lj < rows) m_copy16(dst, P.phi + pbase + li + (long long)sx * lj);
                 else { dst[0] = 0.0; dst[1] = 0.0; }
             }
             if (tid < M_PY4 * (M_PX4 / 4)) {  // 240 chunks of four codes
                 const int lj = tid / (M_PX4 / 4), li = 4 * (tid % (M_PX4 / 4));
-                unsigned *dst = &S.code[m_slot(q, M_RCODE)][li + M_PX4 * lj];
+                unsigned *dst = &S.code[sl_code][li + M_PX4 * lj];
                 if (i0 - 1 + li < sx && j0 - 1 + lj < rows) m_copy16(dst, P.mcode + pbase + li + (long long)sx * lj);
                 else { dst[0] = MCODE_NONE; dst[1] = MCODE_NONE; dst[2] = MCODE_NONE; dst[3] = MCODE_NONE; }
             }
@@ -179,7 +187,7 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
         if (want_s && tid >= 256 && tid < 256 + MARCH_TY * (MARCH_TX / 4)) {  // 128 chunks of four indices
             const int ch = tid - 256;
             const int lj = ch / (MARCH_TX / 4), li = 4 * (ch % (MARCH_TX / 4));
-            int *dst = &S.smap[m_slot(qs, M_RSMAP)][li + MARCH_TX * lj];
+            int *dst = &S.smap[sl_smap][li + MARCH_TX * lj];
             const long long c = cell00 + (long long)sxy * (qs + 3) + (li + 4) + (long long)sx * (lj + 4);
             if (i0 + 3 + li < sx && j0 + 3 + lj < rows) m_copy16(dst, P.smap + c);
             else { dst[0] = -1; dst[1] = -1; dst[2] = -1; dst[3] = -1; }
@@ -190,13 +198,16 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
     MH_FOR_TID(tid) {
         if (tid < 91) S.lawtab[tid] = m_law_from_counts(tid / 13, tid % 13);
         if (tid < 8) S.cnt[tid >> 1][tid & 1] = 0;
-        issue_loads(tid, kA - 4, true, 0, false);
+        issue_loads(tid, kA - 4, true, 0, false, m_slot(kA - 4, M_RPHI), m_slot(kA - 4, M_RCODE), 0);
         m_commit();
-        issue_loads(tid, kA - 3, true, 0, false);
+        issue_loads(tid, kA - 3, true, 0, false, m_slot(kA - 3, M_RPHI), m_slot(kA - 3, M_RCODE), 0);
         m_commit();
     }
 
-    for (int t = kA - 4; t <= kB + 5; t++) {
+    int r_phi = m_slot(kA - 4, M_RPHI), r_code = m_slot(kA - 4, M_RCODE), r_cn = m_slot(kA - 4, M_RCN), r_norm = m_slot(kA - 4, M_RNORM),
+        r_smap = m_slot(kA - 4, M_RSMAP);  // ring slots of plane t
+    for (int t = kA - 4; t <= kB + 5; t++, r_phi = m_rel(r_phi, -1, M_RPHI), r_code = m_rel(r_code, -1, M_RCODE),
+             r_cn = m_rel(r_cn, -1, M_RCN), r_norm = m_rel(r_norm, -1, M_RNORM), r_smap = m_rel(r_smap, -1, M_RSMAP)) {
         const int par = t & 1;
         MH_FOR_TID(tid) { (void)tid; m_wait1(); }
         MH_SYNC();
@@ -209,9 +220,9 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             // K3 (plane t-1): phi on listed solid nodes from the raw phi of their listed fluid neighbours
             if (doK3) {
                 const int n3 = S.cnt[0][par];
-                double *p0 = S.phi[m_slot(t - 1, M_RPHI)];
-                const double *pm = S.phi[m_slot(t - 2, M_RPHI)], *pp = S.phi[m_slot(t, M_RPHI)];
-                const unsigned *cd = S.code[m_slot(t - 1, M_RCODE)];
+                double *p0 = S.phi[m_rel(r_phi, 1, M_RPHI)];
+                const double *pm = S.phi[m_rel(r_phi, 2, M_RPHI)], *pp = S.phi[m_rel(r_phi, 0, M_RPHI)];
+                const unsigned *cd = S.code[m_rel(r_code, 1, M_RCODE)];
                 for (int idx = tid; idx < n3; idx += MARCH_NT) {
                     const int e = S.l3[idx];
                     const unsigned m = cd[e] >> 1;  // bit q <=> neighbour q listed (bits 1..18)
@@ -229,8 +240,8 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             // K6 (plane t-4): normal on listed solid nodes of the 0..n+1 box from the normals of their fluid neighbours
             if (doK6) {
                 const int n6 = S.cnt[1][par];
-                const int s0 = m_slot(t - 4, M_RCN), sm = m_slot(t - 5, M_RCN), sp = m_slot(t - 3, M_RCN);
-                const unsigned *cd = S.code[m_slot(t - 4, M_RCODE)];
+                const int s0 = m_rel(r_cn, 4, M_RCN), sm = m_rel(r_cn, 5, M_RCN), sp = m_rel(r_cn, 3, M_RCN);
+                const unsigned *cd = S.code[m_rel(r_code, 4, M_RCODE)];
                 for (int idx = MARCH_NT - 1 - tid; idx < n6; idx += MARCH_NT) {
                     const int e = S.l6[idx];
                     const unsigned m = cd[e] >> 1;
@@ -254,8 +265,8 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             }
             // task list of K4 (plane t-2): non-solid cells two cells out; every other cell of the region holds n = 0
             if (doL4) {
-                const unsigned *cd = S.code[m_slot(t - 2, M_RCODE)];
-                const int s2 = m_slot(t - 2, M_RCN);
+                const unsigned *cd = S.code[m_rel(r_code, 2, M_RCODE)];
+                const int s2 = m_rel(r_cn, 2, M_RCN);
                 for (int e2 = tid; e2 < ((M_N2 + 31) & ~31); e2 += MARCH_NT) {
                     bool task = false;
                     int e = 0;
@@ -270,7 +281,7 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             }
             // task list of K7 (plane t-5): the column's fluid nodes
             if (doL7) {
-                const int *sm = S.smap[m_slot(t - 5, M_RSMAP)];
+                const int *sm = S.smap[m_rel(r_smap, 5, M_RSMAP)];
                 for (int e0 = tid; e0 < M_N0; e0 += MARCH_NT) {
                     const int a = sm[e0];
                     m_append(a >= 0 && a < P.nA, e0, &S.cnt[3][par], S.l7);
@@ -286,9 +297,9 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             // K4 + K5 (plane t-2)
             if (doL4) {
                 const int n4 = S.cnt[2][par];
-                const double *p0 = S.phi[m_slot(t - 2, M_RPHI)], *pm = S.phi[m_slot(t - 3, M_RPHI)], *pp = S.phi[m_slot(t - 1, M_RPHI)];
-                const unsigned *cd = S.code[m_slot(t - 2, M_RCODE)];
-                const int s2 = m_slot(t - 2, M_RCN), sn = m_slot(t - 2, M_RNORM);
+                const double *p0 = S.phi[m_rel(r_phi, 2, M_RPHI)], *pm = S.phi[m_rel(r_phi, 3, M_RPHI)], *pp = S.phi[m_rel(r_phi, 1, M_RPHI)];
+                const unsigned *cd = S.code[m_rel(r_code, 2, M_RCODE)];
+                const int s2 = m_rel(r_cn, 2, M_RCN), sn = m_rel(r_norm, 2, M_RNORM);
                 const size_t nf = (size_t)P.num_fluid;
                 for (int idx = tid; idx < n4; idx += MARCH_NT) {
                     const int e = S.l4[idx];
@@ -331,9 +342,9 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             // K7 (plane t-5) and the packed output
             if (doL7) {
                 const int n7 = S.cnt[3][par];
-                const int s0 = m_slot(t - 5, M_RCN), sm = m_slot(t - 6, M_RCN), sp = m_slot(t - 4, M_RCN);
-                const double *nrm = S.cnorm[m_slot(t - 5, M_RNORM)];
-                const int *smp = S.smap[m_slot(t - 5, M_RSMAP)];
+                const int s0 = m_rel(r_cn, 5, M_RCN), sm = m_rel(r_cn, 6, M_RCN), sp = m_rel(r_cn, 4, M_RCN);
+                const double *nrm = S.cnorm[m_rel(r_norm, 5, M_RNORM)];
+                const int *smp = S.smap[m_rel(r_smap, 5, M_RSMAP)];
                 for (int idx = MARCH_NT - 1 - tid; idx < n7; idx += MARCH_NT) {
                     const int e0 = S.l7[idx];
                     const int n = smp[e0];
@@ -358,7 +369,7 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
             }
             // task lists of the next phase A
             if (doL3) {
-                const unsigned *cd = S.code[m_slot(t, M_RCODE)];
+                const unsigned *cd = S.code[m_rel(r_code, 0, M_RCODE)];
                 for (int e3 = tid; e3 < ((M_N3 + 31) & ~31); e3 += MARCH_NT) {
                     bool task = false;
                     int e = 0;
@@ -370,7 +381,7 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
                 }
             }
             if (doL6) {
-                const unsigned *cd = S.code[m_slot(t - 3, M_RCODE)];
+                const unsigned *cd = S.code[m_rel(r_code, 3, M_RCODE)];
                 for (int e1 = tid; e1 < ((M_N1 + 31) & ~31); e1 += MARCH_NT) {
                     bool task = false;
                     int e = 0;
@@ -383,7 +394,8 @@ MH_FN void march_block(const Dev &P, MarchSmem &S, const int bx, const int by, c
                 }
             }
             if (tid == 0) { S.cnt[2][par ^ 1] = 0; S.cnt[3][par ^ 1] = 0; }  // lists the next phase A builds
-            issue_loads(tid, t + 2, t + 2 <= kB + 4, t - 3, t - 3 >= kA && t - 3 <= kB);
+            issue_loads(tid, t + 2, t + 2 <= kB + 4, t - 3, t - 3 >= kA && t - 3 <= kB, m_rel(r_phi, -2, M_RPHI), m_rel(r_code, -2, M_RCODE),
+                        m_rel(r_smap, 3, M_RSMAP));
             m_commit();
         }
     }

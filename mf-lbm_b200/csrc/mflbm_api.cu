@@ -157,6 +157,7 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     // shared memory leave room for (stalls: fixed-latency dependencies and the two barriers per plane, no memory stall at
     // all).  The chain is bound by instruction latency, not by bytes.  Opt-in: MFLBM_MARCH=1.
     ctx->march_on = getenv("MFLBM_MARCH") && atoi(getenv("MFLBM_MARCH")) != 0;
+    ctx->march_hybrid = ctx->march_on && atoi(getenv("MFLBM_MARCH")) == 2;
     ctx->march_ready = false;
     ctx->march_reject = 0;
     for (int b = 0; b < 2; b++) {
@@ -765,6 +766,7 @@ static int setup_populations(mflbm_ctx *ctx, const int8_t *walls) {
         for (int m = 0; m < 4; m++)
             if (dev_alloc(ctx, &d.G[m], (size_t)d.nA + 64)) return MFLBM_ERR_CUDA;
     if (!(d.sparse && d.multiphase)) ctx->march_on = false;
+    d.lazy_ok = (ctx->march_on && ctx->march_hybrid) ? 0 : 1;
     if (ctx->march_on) {
         d.mcols_x = (g.nx + MFLBM_MARCH_TX - 1) / MFLBM_MARCH_TX;
         d.mcols_y = (g.ny + MFLBM_MARCH_TY - 1) / MFLBM_MARCH_TY;

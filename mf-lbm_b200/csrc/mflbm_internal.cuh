@@ -153,6 +153,8 @@ struct Dev {
     // class for two consecutive steps is QUIET: every colour gradient there is below the reference's 1e-6 cut-off,
     // i.e. exactly zero, so the gradient chain K3..K6 and the c_norm read of the collision kernel are skipped.
     int use_tiles;
+    int lazy_ok;               // 1: the dense n / |grad phi| arrays hold the previous evaluation, cells that stay below the cut-off
+                               // need not be rewritten (0 with the hybrid chain, see mflbm_ctx::march_hybrid)
     int k4_smem;               // 1: K4 on active tiles stages phi through shared memory (k_gradient_tiles)
     int bc_lo_dyn, bc_hi_dyn;  // 1: the phi ghost planes below k=1 / above k=nz are rewritten every step by an inlet /
                                // outlet kernel or by the halo exchange, and whoever writes them records their phi
@@ -312,7 +314,10 @@ struct mflbm_ctx {
     int res_np[2];
     long long stream_count;             // streamed steps so far
     int flat_bx, flat_by, flat_bz;  // brick of the flat-sweep order (MFLBM_BRICK="bx,by,bz")
-    bool march_on;            // selected for this context (MFLBM_MARCH=0 keeps the list kernels)
+    bool march_on;            // selected for this context (MFLBM_MARCH=1 or 2; otherwise the list kernels)
+    bool march_hybrid;        // MFLBM_MARCH=2: the fused kernel only for the work items around the active tiles; when most
+                              // tiles are active the flat sweeps of the list kernels run (faster there), without their lazy
+                              // shortcuts because the dense arrays are not kept current by the fused kernel
     bool march_ready;         // cell codes built for the current walls / node lists
     int march_reject;         // why the node lists were not accepted (bit mask, 0 = accepted)
     int march_lz_flat;        // planes per work item of the sweeps over everything

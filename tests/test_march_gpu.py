@@ -46,14 +46,15 @@ def _random_phi(wg, wrap_y=False, **kw):
     return o
 
 
-@pytest.mark.parametrize("fused", [1, 0], ids=["march", "lists"])
+@pytest.mark.parametrize("fused", [1, 2, 0], ids=["march", "hybrid", "lists"])
 def test_drainage_front_both_shapes(fused, monkeypatch):
-    """C1-like duct long enough for quiet tiles: first every tile is evaluated, later only the items around the front"""
+    """C1-like duct long enough for quiet tiles: first every tile is evaluated, later only the items around the front
+    (hybrid = MFLBM_MARCH=2: the fused kernel for those items, the flat sweeps of the list kernels for "every tile")"""
     monkeypatch.setenv("MFLBM_MARCH", str(fused))  # (overrides the module fixture)
     wg = geo.sphere_pack(72, 40, 96, periodic=False, porosity=0.4, rmin=4.0, rmax=8.0, seed=21, buffer=6)
     o = make_oracle(nxG=72, nyG=40, nzG=96, la_nu2=0.04, interface_z0=8.0, ca_0=2e-3, walls_global=wg, n_exclude_inlet=6, n_exclude_outlet=6)
     ctx = ctx_from_oracle(o, strict=True, kernel_variant=2)
-    assert ctx.chain_info() == (fused, 0)
+    assert ctx.chain_info() == (1 if fused else 0, 0)
     o.color_gradient(); ctx.color_gradient()
     assert ctx.chain_selfcheck() == 0
     compare_state(ctx, o, 0.0, sparse=True)
@@ -69,9 +70,11 @@ def test_drainage_front_both_shapes(fused, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["march", "hybrid"])
 @pytest.mark.parametrize("dims", [(72, 64, 40), (33, 17, 21), (96, 80, 72)])
-def test_random_phi_periodic(dims):
+def test_random_phi_periodic(dims, mode, monkeypatch):
     """interface everywhere (reference benchmark case 6): the flat shape, tile-unaligned lattices, theta = 150 degrees"""
+    monkeypatch.setenv("MFLBM_MARCH", mode)
     nx, ny, nz = dims
     wg = geo.sphere_pack(nx, ny, nz, periodic=True, porosity=0.45, rmin=3.0, rmax=7.0, seed=5, buffer=0)
     o = _random_phi(wg, kper=1, inlet_BC=0, outlet_BC=0, force_z0=2e-4, la_nu2=0.04, theta_deg=150.0)

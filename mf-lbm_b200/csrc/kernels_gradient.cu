@@ -578,8 +578,9 @@ __global__ void __launch_bounds__(256, MFLBM_PACK_MINB) k_gradient_pack_all(cons
         if (chunk >= nchunk) return;
         const int e = (chunk << 8) + threadIdx.x;
         if (e >= P.nA) continue;
-        const int n = P.aorder ? P.aorder[e] : e;  // flat order (bricks): the chunk's stencils overlap in y and z as well
-        const int c = P.cellA[n];
+        // brick order (MFLBM_BRICK7): the chunk's stencils overlap in y and z as well; cell and node index are independent loads
+        const int n = P.aorder ? P.aorder[e] : e;
+        const int c = P.aorder ? P.acell[e] : P.cellA[e];
         const double cnorm = P.c_norm[c];
         double cnx = 0.0, cny = 0.0, cnz = 0.0, tmp = 0.0;
         if (cnorm != 0.0) {

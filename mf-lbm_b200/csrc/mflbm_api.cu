@@ -168,6 +168,11 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->stream_count = 0;
     // order of the flat sweeps of the gradient chain (Dev::gcell_r): bricks of bx x by x bz cells; bx = 0: as wide as the lattice
     ctx->flat_bx = 0; ctx->flat_by = 1; ctx->flat_bz = 1;
+    ctx->k7_bx = 0; ctx->k7_by = 1; ctx->k7_bz = 1;
+    if (const char *b = getenv("MFLBM_BRICK7")) {
+        int x = 0, y = 1, z = 1;
+        if (sscanf(b, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1 && z >= 1) { ctx->k7_bx = x; ctx->k7_by = y; ctx->k7_bz = z; }
+    }
     if (const char *b = getenv("MFLBM_BRICK")) {
         int x = 0, y = 1, z = 1;
         if (sscanf(b, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1 && z >= 1) { ctx->flat_bx = x; ctx->flat_by = y; ctx->flat_bz = z; }
@@ -380,9 +385,9 @@ static void sort_by_tile(const std::vector<int> &tile, int ntiles, std::vector<i
 
 // Order of the flat sweeps (Dev::gcell_r): stable counting sort of a list of cells by brick, so that a list that comes in
 // raster order keeps it inside every brick.  order[r] = position in the input of the r-th entry in flat order.
-static void flat_order(const mflbm_ctx *ctx, const int *cells, size_t n, std::vector<int> &order) {
+static void flat_order(const mflbm_ctx *ctx, const int *cells, size_t n, std::vector<int> &order, bool k7 = false) {
     const Grid &g = ctx->d.g;
-    const int bx = ctx->flat_bx, by = ctx->flat_by, bz = ctx->flat_bz;
+    const int bx = k7 ? ctx->k7_bx : ctx->flat_bx, by = k7 ? ctx->k7_by : ctx->flat_by, bz = k7 ? ctx->k7_bz : ctx->flat_bz;
     const int nbx = bx > 0 ? (g.sx + bx - 1) / bx : 1, nby = (g.ny + 8 + by - 1) / by, nbz = (g.nz + 8 + bz - 1) / bz;
     std::vector<int> brick(n), start;
 #pragma omp parallel for schedule(static)
@@ -669,12 +674,17 @@ static int build_active_set(mflbm_ctx *ctx, const int8_t *walls /* (-1:n+2)^3, i
 #pragma omp parallel for schedule(static)
             for (long long n = 0; n < nG; n++) sorted[(size_t)n] = gcell[(size_t)order[(size_t)n]];
             CU(cudaMemcpy(d.gcell_r, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice));
-            if (nA > 0) {  // K7 + packing walk the fluid nodes in the same order
-                flat_order(ctx, cellA.data(), (size_t)nA, order);
-                if (dev_alloc(ctx, &d.aorder, (size_t)nA, false)) return MFLBM_ERR_CUDA;
-                CU(cudaMemcpy(d.aorder, order.data(), (size_t)nA * sizeof(int), cudaMemcpyHostToDevice));
-            }
         }
+    }
+    d.aorder = d.acell = nullptr;
+    if (d.use_tiles && nA > 0 && !(ctx->k7_bx == 0 && ctx->k7_by == 1 && ctx->k7_bz == 1)) {  // K7 + packing in brick order
+        std::vector<int> order, cells((size_t)nA);
+        flat_order(ctx, cellA.data(), (size_t)nA, order, true);
+#pragma omp parallel for schedule(static)
+        for (int n = 0; n < nA; n++) cells[(size_t)n] = cellA[(size_t)order[(size_t)n]];
+        if (dev_alloc(ctx, &d.aorder, (size_t)nA, false) || dev_alloc(ctx, &d.acell, (size_t)nA, false)) return MFLBM_ERR_CUDA;
+        CU(cudaMemcpy(d.aorder, order.data(), (size_t)nA * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.acell, cells.data(), (size_t)nA * sizeof(int), cudaMemcpyHostToDevice));
     }
     if (d.use_tiles && nG > 0) {  // tile-driven gradient chain: gcell grouped by tile (raster order inside a tile)
         std::vector<int> tile((size_t)nG), order, start;

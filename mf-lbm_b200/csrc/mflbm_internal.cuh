@@ -137,7 +137,8 @@ struct Dev {
     int *gk5;         // the same for gcell and the fluid boundary list grouped by tile (tile-driven K4)
     int nG;
     // the node lists and the active nodes in flat order (see gcell_r), for the flat sweeps of K3 / K6 / K7
-    int *solid_cell_r, *fluid_cell_r, *aorder;  // aorder[e] = active index of the e-th fluid node in flat order
+    int *solid_cell_r, *fluid_cell_r;
+    int *aorder, *acell;  // K7 + packing in brick order (MFLBM_BRICK7): active index / dense cell of the e-th fluid node
     unsigned *solid_mask_r;
     double *solid_law_r, *fluid_nw_r;
     int full_curv;    // 1: curvature at all nodes like the reference (MP/Phase_gradient.F90:121); 0: fluid nodes only
@@ -314,6 +315,7 @@ struct mflbm_ctx {
     int res_np[2];
     long long stream_count;             // streamed steps so far
     int flat_bx, flat_by, flat_bz;  // brick of the flat-sweep order (MFLBM_BRICK="bx,by,bz")
+    int k7_bx, k7_by, k7_bz;        // brick order of K7 + packing alone (MFLBM_BRICK7; 0,1,1 = the node order itself)
     bool march_on;            // selected for this context (MFLBM_MARCH=1 or 2; otherwise the list kernels)
     bool march_hybrid;        // MFLBM_MARCH=2: the fused kernel only for the work items around the active tiles; when most
                               // tiles are active the flat sweeps of the list kernels run (faster there), without their lazy

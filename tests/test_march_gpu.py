@@ -119,12 +119,15 @@ def test_foreign_node_lists_fall_back_to_the_list_kernels():
     ctx.close()
 
 
-@pytest.mark.parametrize("brick", ["", "32,8,4", "16,4,2", "0,4,4"], ids=["raster", "b32x8x4", "b16x4x2", "rows4x4"])
+@pytest.mark.parametrize("brick", ["", "32,8,4", "16,4,2", "0,4,4", "k7:96,4,2", "k7:24,2,3"],
+                         ids=["raster", "b32x8x4", "b16x4x2", "rows4x4", "k7_96x4x2", "k7_24x2x3"])
 def test_flat_sweeps_of_the_list_kernels(brick, monkeypatch):
     """the default chain (list kernels) in its flat shape -- every tile holds an interface: K4 + K5 fused in one sweep, the lists
     walked in brick order (MFLBM_BRICK) -- against the oracle and against the separate reference-order kernels (self-check)"""
     monkeypatch.setenv("MFLBM_MARCH", "0")
-    if brick:
+    if brick.startswith("k7:"):  # K7 + packing alone in brick order
+        monkeypatch.setenv("MFLBM_BRICK7", brick[3:])
+    elif brick:
         monkeypatch.setenv("MFLBM_BRICK", brick)
     wg = geo.sphere_pack(72, 64, 40, periodic=True, porosity=0.45, rmin=3.0, rmax=7.0, seed=5, buffer=0)
     o = _random_phi(wg, kper=1, inlet_BC=0, outlet_BC=0, force_z0=2e-4, la_nu2=0.04, theta_deg=150.0)

@@ -168,6 +168,7 @@ extern "C" int mflbm_create(const mflbm_config *cfg, mflbm_ctx **out) {
     ctx->stream_count = 0;
     // order of the flat sweeps of the gradient chain (Dev::gcell_r): bricks of bx x by x bz cells; bx = 0: as wide as the lattice
     ctx->flat_bx = 0; ctx->flat_by = 1; ctx->flat_bz = 1;
+    ctx->pdl = getenv("MFLBM_PDL") && atoi(getenv("MFLBM_PDL")) != 0;
     ctx->k7_bx = 0; ctx->k7_by = 1; ctx->k7_bz = 1;
     if (const char *b = getenv("MFLBM_BRICK7")) {
         int x = 0, y = 1, z = 1;

@@ -314,6 +314,7 @@ struct mflbm_ctx {
     cudaEvent_t ev_win[2], ev_res[2], ev_step[2];
     int res_np[2];
     long long stream_count;             // streamed steps so far
+    bool pdl;                       // collision / wrap kernels launched with programmatic stream serialization (MFLBM_PDL)
     int flat_bx, flat_by, flat_bz;  // brick of the flat-sweep order (MFLBM_BRICK="bx,by,bz")
     int k7_bx, k7_by, k7_bz;        // brick order of K7 + packing alone (MFLBM_BRICK7; 0,1,1 = the node order itself)
     bool march_on;            // selected for this context (MFLBM_MARCH=1 or 2; otherwise the list kernels)
